@@ -1,0 +1,134 @@
+"""The oracle (oracle/audiodec_oracle.py) against the golden vectors dumped from the
+unmodified reference (tests/golden/make_golden.py).  CPU only.
+
+Tolerances: the oracle issues the same torch CPU ops as the reference, so in the build
+container the match is bit-exact; on another host CPU (the GPU box) oneDNN/MKL may pick
+different kernels, so waveforms are compared at 2e-5 max-abs and indices must still be
+bit-identical (the goldens' smallest relative top-2 margin is 6.9e-5, far above conv
+rounding noise)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from audiodec_b200 import synthetic as S
+from oracle import audiodec_oracle as O
+
+TOL = 2e-5
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def test_weights_regenerate_bit_identically(golden_dir, symad_sd, hifigan_sd):
+    g = _load(golden_dir, "v1_oneshot.npz")
+    assert S.state_dict_digest(symad_sd) == str(g["enc_digest"])
+    assert S.state_dict_digest(hifigan_sd) == str(g["dec_digest"])
+
+
+def test_symad_oneshot(golden_dir, symad_sd):
+    g = _load(golden_dir, "symad_oneshot.npz")
+    fresh = O.SymADOracle(S.SYMAD_PARAMS, symad_sd)
+    zq0 = fresh.initial_encoder(8192)
+    assert zq0.shape == (1, 28, 64)
+    np.testing.assert_allclose(zq0.numpy(), g["warm_zq"], atol=TOL)
+    c = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
+    z, idx, zq, y = c.run(torch.from_numpy(g["x"]))
+    assert idx.dtype == torch.int64 and tuple(idx.shape) == (8, 40)
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(z.numpy(), g["z"], atol=TOL)
+    np.testing.assert_allclose(zq.numpy(), g["zq"], atol=TOL)
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=TOL)
+
+
+def test_symad_stream_chunks(golden_dir, symad_sd):
+    g = _load(golden_dir, "symad_stream.npz")
+    c = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
+    x = torch.from_numpy(g["x"])
+    n = int(g["chunk"])
+    outs = [c.run(x[:, :, i:i + n]) for i in range(0, x.shape[-1], n)]
+    np.testing.assert_array_equal(torch.cat([o[1] for o in outs], -1).numpy(), g["idx"])
+    np.testing.assert_allclose(torch.cat([o[3] for o in outs], -1).numpy(), g["y"], atol=TOL)
+    # chunk invariance: streamed == one-shot
+    one = _load(golden_dir, "symad_oneshot.npz")
+    np.testing.assert_array_equal(g["idx"], one["idx"])
+    np.testing.assert_allclose(g["y"], one["y"], atol=5e-6)
+
+
+def test_symad_ragged_length(golden_dir, symad_sd):
+    g = _load(golden_dir, "symad_ragged.npz")
+    c = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
+    z, idx, zq, y = c.run(torch.from_numpy(g["x"]))
+    assert z.shape[-1] == 14 and y.shape[-1] == 4200      # floor((T-1)/s)+1 per stage, T=4001
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=TOL)
+
+
+def test_symad_batch3(golden_dir, symad_sd):
+    g = _load(golden_dir, "symad_batch3.npz")
+    c = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
+    z, idx, zq, y = c.run(torch.from_numpy(g["x"]))
+    assert tuple(idx.shape) == (8, 3, 20) and tuple(zq.shape) == (3, 20, 64)
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(zq.numpy(), g["zq"], atol=TOL)
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=TOL)
+
+
+def test_v1_vocoder(golden_dir, symad_sd, hifigan_sd):
+    g = _load(golden_dir, "v1_oneshot.npz")
+    c = O.CodecOracle(S.SYMAD_PARAMS, symad_sd, S.HIFIGAN_V1_PARAMS, hifigan_sd)
+    z, idx, zq, y = c.run(torch.from_numpy(g["x"]))
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=TOL)
+    gs = _load(golden_dir, "v1_stream.npz")
+    c = O.CodecOracle(S.SYMAD_PARAMS, symad_sd, S.HIFIGAN_V1_PARAMS, hifigan_sd)
+    x = torch.from_numpy(gs["x"])
+    ys = [c.run(x[:, :, i:i + 1500])[3] for i in range(0, x.shape[-1], 1500)]
+    np.testing.assert_allclose(torch.cat(ys, -1).numpy(), gs["y"], atol=TOL)
+
+
+def _case(g, name):
+    return {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+
+
+@pytest.mark.parametrize("name", ["conv_k7_d3", "conv_k6_s3", "conv_k10_s5_ragged", "conv_k11_d5_g3", "conv_short_chunk"])
+def test_layer_causal_conv(golden_dir, name):
+    c = _case(_load(golden_dir, "layers.npz"), name)
+    cin, cout, k, s, d, grp, T = [int(v) for v in c["cfg"]]
+    state = torch.zeros(1, cin, (k - 1) * d)
+    w, b = torch.from_numpy(c["w"]), torch.from_numpy(c["b"])
+    for xi, yi in (("x0", "y0"), ("x1", "y1")):
+        y, state = O.causal_conv1d_infer(torch.from_numpy(c[xi]), w, b, state, s, d, grp)
+        assert y.shape[-1] == (T - 1) // s + 1
+        np.testing.assert_allclose(y.numpy(), c[yi], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["convtr_s5", "convtr_s3"])
+def test_layer_causal_convtr(golden_dir, name):
+    c = _case(_load(golden_dir, "layers.npz"), name)
+    cin, cout, k, s, _, _, T = [int(v) for v in c["cfg"]]
+    state = torch.zeros(1, cin, 1)
+    w, b = torch.from_numpy(c["w"]), torch.from_numpy(c["b"])
+    for xi, yi in (("x0", "y0"), ("x1", "y1")):
+        x = torch.from_numpy(c[xi])
+        prev = state
+        y, state = O.causal_convtr1d_infer(x, w, b, state, s)
+        np.testing.assert_allclose(y.numpy(), c[yi], atol=1e-6)
+        # two-tap closed form: y[j*s+r] = b + W[:,:,r]^T x[j] + W[:,:,s+r]^T x[j-1]
+        xx = torch.cat((prev, x), -1)[0]
+        for j in range(T):
+            for r in range(s):
+                ref = b + w[:, :, r].T @ xx[:, j + 1] + w[:, :, s + r].T @ xx[:, j]
+                np.testing.assert_allclose(ref.numpy(), c[yi][0, :, j * s + r], atol=2e-6)
+
+
+def test_layer_rvq(golden_dir):
+    c = _case(_load(golden_dir, "layers.npz"), "rvq")
+    embeds = [torch.from_numpy(e) for e in c["embeds"]]
+    zq, idx = O.rvq_forward_index(torch.from_numpy(c["x"]), embeds, True)
+    np.testing.assert_array_equal(idx.squeeze(1).numpy(), c["idx"])
+    np.testing.assert_allclose(zq.numpy(), c["zq"], atol=1e-6)
+    cb = torch.stack([e.T for e in embeds]).reshape(-1, 16)
+    np.testing.assert_allclose(O.rvq_lookup(idx.squeeze(1), cb).numpy(), c["lookup"], atol=1e-6)

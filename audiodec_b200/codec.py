@@ -1,0 +1,273 @@
+"""Host-side mirrors of the reference's streaming generators, backed by the C-ABI library.
+
+``SymADStreamGenerator`` stands in for ``models/autoencoder/AudioDec.py:166 StreamGenerator`` and
+``HiFiGANStreamGenerator`` for ``models/vocoder/HiFiGAN.py:222 StreamGenerator``: same constructor
+keywords (``config.yml`` ``generator_params``), same methods with the same tensor shapes
+(``load_state_dict / eval / to / initial_encoder / initial_decoder / encode / quantize / lookup /
+decode / reset_buffer``), so the objects can be returned from ``AudioCodec._load_encoder /
+_load_decoder`` (bin/stream.py:38-45) unchanged.  All arithmetic happens in hand-written sm_100a
+kernels (audiodec_b200/csrc); torch only provides device memory and the current stream.
+
+Differences from the reference, all extensions:
+  * batches: the reference's streaming state is (1,C,P) so only B=1 works (layers/conv_layer.py:144-146);
+    here a batch of B independent streams is allowed.  A handle warmed with one stream replicates its
+    state when first called with B>1.  ``quantize`` then returns (Nq,B,F) (what
+    ``ResidualVQ.forward_index`` yields before its ``squeeze(1)``, vq_module.py:148-149) and ``lookup``
+    returns (B,F,D).
+  * there is no CPU path: ``.to('cpu')`` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _check(rc, handle):
+    if rc != 0:
+        raise RuntimeError("audiodec_b200: " + _lib.last_error(handle))
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _fill(arr, values):
+    for i, v in enumerate(values):
+        arr[i] = int(v)
+
+
+class _StreamGeneratorBase:
+    """Common plumbing: deferred handle creation (weights arrive before the device is known, exactly
+    like ``Generator(**params)`` -> ``load_state_dict`` -> ``.to(device)`` in the reference)."""
+
+    def __init__(self):
+        self._lib = _lib.load()
+        self._cfg = _lib.AdecConfig()
+        self._sd = None
+        self._h = None
+        self._device = None
+
+    # -- torch.nn.Module look-alikes ------------------------------------------------------------
+    def load_state_dict(self, state_dict, strict=True):
+        self._sd = {k: v.detach().to(torch.float32).cpu().contiguous() for k, v in state_dict.items()}
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("audiodec_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self._sd is None:
+            raise RuntimeError("load_state_dict must be called before .to(device)")
+        if self._h is not None:
+            if device.index not in (None, self._device.index):
+                raise RuntimeError("handle already lives on " + str(self._device))
+            return self
+        index = device.index if device.index is not None else torch.cuda.current_device()
+        self._device = torch.device("cuda", index)
+        h = ctypes.c_void_p()
+        rc = self._lib.adec_create(ctypes.byref(self._cfg), index, ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError("audiodec_b200: " + _lib.last_error(None))
+        self._h = h
+        for key, t in self._sd.items():
+            shape = (ctypes.c_int64 * t.dim())(*t.shape)
+            _check(self._lib.adec_set_tensor(h, key.encode(), _ptr(t), shape, t.dim()), h)
+        _check(self._lib.adec_finalize(h), h)
+        self._sd = None
+        return self
+
+    def __del__(self):
+        try:
+            if self._h is not None:
+                self._lib.adec_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    # -- helpers ------------------------------------------------------------------------------------
+    def _ready(self):
+        if self._h is None:
+            raise RuntimeError("call .to('cuda:N') before using the codec")
+
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self._device).cuda_stream)
+
+    def _in(self, t, dtype=torch.float32):
+        if t.device != self._device:
+            raise RuntimeError(f"input is on {t.device}, codec is on {self._device}")
+        return t.to(dtype).contiguous()
+
+    def _batch(self, b):
+        n = self._lib.adec_n_streams(self._h)
+        if n != b:
+            _check(self._lib.adec_set_streams(self._h, b), self._h)
+
+    @property
+    def n_streams(self):
+        self._ready()
+        return self._lib.adec_n_streams(self._h)
+
+    @property
+    def launch_count(self):
+        return int(self._lib.adec_launch_count(self._h)) if self._h is not None else 0
+
+    def reset_buffer(self):
+        """AudioDec.py:250-256 / HiFiGAN.py:298-305."""
+        self._ready()
+        _check(self._lib.adec_reset(self._h, self._stream()), self._h)
+
+
+class SymADStreamGenerator(_StreamGeneratorBase):
+    """models/autoencoder/AudioDec.py:166-256."""
+
+    def __init__(self, input_channels=1, output_channels=1, encode_channels=32, decode_channels=32, code_dim=64,
+                 codebook_num=8, codebook_size=1024, bias=True, enc_ratios=(2, 4, 8, 16), dec_ratios=(16, 8, 4, 2),
+                 enc_strides=(3, 4, 5, 5), dec_strides=(5, 5, 4, 3), mode="causal", codec="audiodec",
+                 projector="conv1d", quantier="residual_vq", nonlinear_activation="ELU",
+                 nonlinear_activation_params={}, use_weight_norm=False):
+        super().__init__()
+        assert mode == "causal", f"Mode {mode} does not support streaming!"       # models/utils.py:13-15
+        if codec != "audiodec":
+            raise NotImplementedError(f"Codec ({codec}) is not supported!")          # AudioDec.py:59-60 (symAAD: next)
+        if projector != "conv1d" or quantier != "residual_vq":
+            raise NotImplementedError("only projector='conv1d', quantier='residual_vq' are built")
+        if nonlinear_activation != "ELU" or nonlinear_activation_params:
+            raise NotImplementedError("only ELU(alpha=1) residual units are built")
+        c = self._cfg
+        c.model_type = _lib.MODEL_SYMAD
+        c.input_channels, c.output_channels = input_channels, output_channels
+        c.encode_channels, c.decode_channels = encode_channels, decode_channels
+        c.code_dim, c.codebook_num, c.codebook_size = code_dim, codebook_num, codebook_size
+        c.bias = int(bias)
+        c.n_enc, c.n_dec = len(enc_strides), len(dec_strides)
+        _fill(c.enc_ratios, enc_ratios), _fill(c.enc_strides, enc_strides)
+        _fill(c.dec_ratios, dec_ratios), _fill(c.dec_strides, dec_strides)
+        c.use_weight_norm = int(use_weight_norm)
+        self.input_channels = input_channels
+        self.code_dim, self.codebook_num = code_dim, codebook_num
+
+    # -- streaming API ---------------------------------------------------------------------------------
+    def initial_encoder(self, receptive_length, device):
+        """AudioDec.py:216-221: push `receptive_length` zeros through encode/quantize/lookup."""
+        self._ready()
+        z = self.encode(torch.zeros(1, self.input_channels, receptive_length, device=self._device))
+        return self.lookup(self.quantize(z))
+
+    def initial_decoder(self, zq):
+        self.decode(zq)                                                              # AudioDec.py:224-225
+
+    def encode(self, x):
+        """(B,1,T) float -> z (B,code_dim,F)   (AudioDec.py:228-234)"""
+        self._ready()
+        if x.dim() != 3:
+            raise RuntimeError("encode expects (batch, channel, length)")
+        if x.size(1) != self.input_channels:
+            x = x.reshape(-1, self.input_channels, x.size(-1))
+        x = self._in(x)
+        b, _, t = x.shape
+        self._batch(b)
+        f = self._lib.adec_frames_for(self._h, t)
+        z = torch.empty(b, self.code_dim, f, device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_encode(self._h, _ptr(x), b, t, _ptr(z), self._stream()), self._h)
+        return z
+
+    def quantize(self, z):
+        """z (B,code_dim,F) -> idx int64 (Nq,F) for B==1 else (Nq,B,F)   (AudioDec.py:237-239)"""
+        self._ready()
+        z = self._in(z)
+        b, _, f = z.shape
+        idx = torch.empty(self.codebook_num, b, f, device=self._device, dtype=torch.int64)
+        _check(self._lib.adec_quantize(self._h, _ptr(z), b, f, _ptr(idx), self._stream()), self._h)
+        return idx.squeeze(1) if b == 1 else idx
+
+    def lookup(self, idx):
+        """idx (Nq,F) -> zq (1,F,D); (Nq,B,F) -> (B,F,D)   (AudioDec.py:242-243)"""
+        self._ready()
+        idx = self._in(idx, torch.int64)
+        if idx.dim() == 2:
+            idx = idx.unsqueeze(1)
+        _, b, f = idx.shape
+        zq = torch.empty(b, f, self.code_dim, device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_lookup(self._h, _ptr(idx), b, f, _ptr(zq), self._stream()), self._h)
+        return zq
+
+    def decode(self, zq):
+        """zq (B,F,D) channels-last -> y (B,1,F*hop)   (AudioDec.py:246-247)"""
+        self._ready()
+        zq = self._in(zq)
+        b, f, _ = zq.shape
+        self._batch(b)
+        y = torch.empty(b, 1, f * self._lib.adec_hop_length(self._h), device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_decode(self._h, _ptr(zq), b, f, _ptr(y), self._stream()), self._h)
+        return y
+
+
+class HiFiGANStreamGenerator(_StreamGeneratorBase):
+    """models/vocoder/HiFiGAN.py:222-305 (AD v1: groups>1 and a single resblock kernel -> MultiGroupConv1d)."""
+
+    def __init__(self, in_channels=80, out_channels=1, channels=512, kernel_size=7, upsample_scales=(8, 8, 2, 2),
+                 upsample_kernel_sizes=(16, 16, 4, 4), resblock_kernel_sizes=(3, 7, 11),
+                 resblock_dilations=[(1, 3, 5), (1, 3, 5), (1, 3, 5)], groups=1, bias=True, use_additional_convs=True,
+                 nonlinear_activation="LeakyReLU", nonlinear_activation_params={"negative_slope": 0.1},
+                 use_weight_norm=True, stats=None):
+        super().__init__()
+        assert kernel_size % 2 == 1, "Kernel size must be odd number."               # HiFiGAN.py:73-75
+        assert len(upsample_scales) == len(upsample_kernel_sizes)
+        assert len(resblock_dilations) == len(resblock_kernel_sizes)
+        if not (len(resblock_kernel_sizes) == 1 and groups > 1):
+            raise NotImplementedError("only the MultiGroupConv1d generator (AD v1/v2 style) is built; v0 is 'next'")
+        if nonlinear_activation != "LeakyReLU" or not use_additional_convs or not bias:
+            raise NotImplementedError("only LeakyReLU + additional convs + bias is built")
+        c = self._cfg
+        c.model_type = _lib.MODEL_HIFIGAN
+        c.in_channels, c.out_channels, c.channels, c.kernel_size = in_channels, out_channels, channels, kernel_size
+        c.n_up = len(upsample_scales)
+        _fill(c.upsample_scales, upsample_scales), _fill(c.upsample_kernel_sizes, upsample_kernel_sizes)
+        c.resblock_kernel_size = resblock_kernel_sizes[0]
+        c.n_dil = len(resblock_dilations[0])
+        _fill(c.resblock_dilations, resblock_dilations[0])
+        c.groups = groups
+        c.negative_slope = float(nonlinear_activation_params.get("negative_slope", 0.01))
+        c.use_weight_norm = int(use_weight_norm)
+        c.has_stats = int(stats is not None)       # mean/scale themselves come from the state dict (HiFiGAN.py:206-219)
+        self.in_channels = in_channels
+
+    def initial_decoder(self, c):
+        self.decode(c)                                                                # HiFiGAN.py:264-265
+
+    def decode(self, c):
+        """zq (B,F,in_channels) channels-last -> y (B,1,F*prod(scales)) in (-1,1)   (HiFiGAN.py:268-296)"""
+        self._ready()
+        c = self._in(c)
+        b, f, _ = c.shape
+        self._batch(b)
+        y = torch.empty(b, 1, f * self._lib.adec_hop_length(self._h), device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_decode(self._h, _ptr(c), b, f, _ptr(y), self._stream()), self._h)
+        return y
+
+
+def codec_host(encoder: SymADStreamGenerator, decoder, x_host: torch.Tensor, want_idx=True):
+    """Whole path on HOST buffers through ``adec_codec_host`` (H2D + encode + quantize + lookup + decode +
+    D2H), i.e. what demoFile.py:55-62 does around the four calls.  x_host: (B,1,T) float32 CPU tensor
+    (pinned for full PCIe speed).  Returns (idx (Nq,B,F) int64 CPU or None, y (B,1,F*hop) float32 CPU)."""
+    encoder._ready(), decoder._ready()
+    assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
+    b, _, t = x_host.shape
+    encoder._batch(b)
+    if decoder is not encoder:
+        decoder._batch(b)
+    lib = encoder._lib
+    f = lib.adec_frames_for(encoder._h, t)
+    hop = lib.adec_hop_length(decoder._h)
+    pin = x_host.is_pinned()
+    idx = torch.empty(encoder.codebook_num, b, f, dtype=torch.int64, pin_memory=pin) if want_idx else None
+    y = torch.empty(b, 1, f * hop, dtype=torch.float32, pin_memory=pin)
+    _check(lib.adec_codec_host(encoder._h, decoder._h, _ptr(x_host), b, t, _ptr(idx) if want_idx else None,
+                               _ptr(y), encoder._stream()), encoder._h)
+    return idx, y

@@ -1,0 +1,1047 @@
+// audiodec_b200 host side: model plans, weight ingest/packing, the C ABI (include/audiodec_b200.h).
+//
+// The reference builds torch modules from config.yml and runs ~60 nn.Conv1d calls per encode/decode,
+// each preceded by a torch.cat of its pad_buffer (layers/conv_layer.py:153-156).  Here a model is a
+// flat list of `Op`s over three ping-pong activation buffers in HBM (channels-last), each Op one
+// kernel launch that reads its causal history from a per-stream state buffer and writes the next one.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/audiodec_b200.h"
+#include "kernels.cuh"
+
+using namespace adec;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+std::string fmt(const char* f, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, f);
+    vsnprintf(buf, sizeof buf, f, ap);
+    va_end(ap);
+    return buf;
+}
+
+struct HostTensor {
+    std::vector<int64_t> shape;
+    std::vector<float> data;
+    int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+bool is_pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch table
+// ------------------------------------------------------------------------------------------------
+typedef cudaError_t (*ConvLaunchFn)(const ConvArgs&, dim3, int, cudaStream_t);
+
+template <int CW, int CO, int TT, int KC, bool F>
+cudaError_t launch_conv(const ConvArgs& a, dim3 grid, int window_rows, cudaStream_t s) {
+    using Cfg = ConvCfg<CW, CO, TT, KC>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kern = conv_gemm_kernel<CW, CO, TT, KC, F>;
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const size_t smem = Cfg::smem_bytes(window_rows);
+    if (smem > 227 * 1024) return cudaErrorInvalidConfiguration;
+    kern<<<grid, Cfg::NTHREADS, smem, s>>>(a);
+    return cudaGetLastError();
+}
+
+struct ConvKernelCfg { int CW, CO, TT, KC; bool fuse; ConvLaunchFn fn; };
+
+#define ADEC_PLAIN(CW) \
+    {CW, 256, 64, 8, false, launch_conv<CW, 256, 64, 8, false>}, \
+    {CW, 128, 64, 16, false, launch_conv<CW, 128, 64, 16, false>}, \
+    {CW, 64, 128, 32, false, launch_conv<CW, 64, 128, 32, false>}, \
+    {CW, 32, 256, 32, false, launch_conv<CW, 32, 256, 32, false>}
+
+const ConvKernelCfg kConvKernels[] = {
+    ADEC_PLAIN(32), ADEC_PLAIN(64), ADEC_PLAIN(96), ADEC_PLAIN(128), ADEC_PLAIN(256),
+    {32, 32, 256, 32, true, launch_conv<32, 32, 256, 32, true>},
+    {64, 64, 128, 32, true, launch_conv<64, 64, 128, 32, true>},
+    {128, 128, 64, 16, true, launch_conv<128, 128, 64, 16, true>},
+    {256, 256, 64, 8, true, launch_conv<256, 256, 64, 8, true>},
+};
+
+const ConvKernelCfg* find_conv_kernel(int CW, int CO, bool fuse) {
+    for (const auto& k : kConvKernels)
+        if (k.CW == CW && k.CO == CO && k.fuse == fuse) return &k;
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Op: one kernel launch of the plan
+// ------------------------------------------------------------------------------------------------
+enum OpKind { OP_STEM, OP_CONV, OP_HEAD };
+enum { BUF_EXT_IN = -10, BUF_EXT_OUT = -11, BUF_NONE = -1 };
+
+struct Op {
+    OpKind kind = OP_CONV;
+    std::string name;
+    // logical description (per group, after channel padding)
+    int G = 1, Cin = 0, Cin_eff = 0, Cout = 0, Ktaps = 1, dil = 1, RG = 1;
+    int P = 0;        // history rows (of x~)
+    int down = 1;     // Tout = (T-1)/down + 1
+    int up = 1;       // rows after reinterpretation = Tout*up (transposed conv)
+    bool fuse = false, shared_in = false, out_nct = false, post_tanh = false;
+    int pre_act = ACT_NONE, mid_act = ACT_NONE;
+    float slope = 0.f;
+    // host weights until finalize
+    std::vector<float> weff;    // [G][Ktaps][Cin_eff][Cout]
+    std::vector<float> weff2;   // fuse: [Cout][Cout] as [ci][co]
+    std::vector<float> hbias;   // [G*Cout] or empty
+    std::vector<float> hstate;  // initial state (P, st_C) or empty (zeros)
+    // kernel config
+    const ConvKernelCfg* kc = nullptr;
+    int n_pieces = 1, n_co_tiles = 1;
+    // device
+    float *w = nullptr, *w2 = nullptr, *bias = nullptr;
+    const float *mean = nullptr, *scale = nullptr;
+    float head_bias = 0.f;
+    long long w_tile_floats = 0;
+    int st_C = 0, st_groups = 1;
+    float* st[2] = {nullptr, nullptr};
+    int cur = 0;
+    // wiring
+    int in_buf = BUF_NONE, out_buf = BUF_NONE, res_buf = BUF_NONE;
+    int ldx = 0, x_goff = 0, ldy = 0, y_goff = 0, ldr = 0, r_goff = 0;
+};
+
+struct DevBuf {
+    float* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct adec_handle {
+    adec_config cfg{};
+    int device = 0;
+    bool finalized = false;
+    std::string err;
+    std::map<std::string, HostTensor> tensors;
+    std::set<std::string> consumed;
+    std::vector<Op> enc_ops, dec_ops;
+    int n_streams = 1;
+    DevBuf ws[3];
+    std::vector<void*> owned;     // device allocations freed in destroy
+    // rvq
+    float *d_embed = nullptr, *d_e2 = nullptr, *d_codebook = nullptr;
+    float *d_mean = nullptr, *d_scale = nullptr;
+    int* d_err = nullptr;
+    int64_t launches = 0;
+    // host-path scratch
+    DevBuf hx, hz, hzq, hy;
+    long long* hidx = nullptr;
+    size_t hidx_cap = 0;
+
+    int fail(const std::string& m) { err = m; return 1; }
+};
+
+namespace {
+
+#define CK(h, call)                                                                        \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess) return (h)->fail(fmt("%s failed: %s", #call, cudaGetErrorString(e_))); \
+    } while (0)
+
+int dev_alloc(adec_handle* h, float** p, size_t n_floats) {
+    CK(h, cudaMalloc((void**)p, std::max<size_t>(n_floats, 4) * sizeof(float)));
+    h->owned.push_back(*p);
+    return 0;
+}
+
+int dev_upload(adec_handle* h, float** p, const std::vector<float>& v) {
+    if (dev_alloc(h, p, v.size())) return 1;
+    if (!v.empty()) CK(h, cudaMemcpy(*p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int ensure(adec_handle* h, DevBuf& b, size_t n_floats) {
+    if (b.cap >= n_floats) return 0;
+    if (b.p) CK(h, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    CK(h, cudaMalloc((void**)&b.p, n_floats * sizeof(float)));
+    b.cap = n_floats;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight access (state-dict keys), weight-norm folding
+// ------------------------------------------------------------------------------------------------
+const HostTensor* find(adec_handle* h, const std::string& key) {
+    auto it = h->tensors.find(key);
+    if (it == h->tensors.end()) return nullptr;
+    h->consumed.insert(key);
+    return &it->second;
+}
+
+// returns the effective weight for "<prefix>.weight" or folds "<prefix>.weight_g/_v"
+// (torch.nn.utils.weight_norm, dim=0: w = v * (g / ||v||), norm over all dims but 0; HiFiGAN.py:193-203)
+int get_weight(adec_handle* h, const std::string& prefix, HostTensor* out) {
+    if (const HostTensor* w = find(h, prefix + ".weight")) { *out = *w; return 0; }
+    const HostTensor* g = find(h, prefix + ".weight_g");
+    const HostTensor* v = find(h, prefix + ".weight_v");
+    if (!g || !v) return h->fail("missing key " + prefix + ".weight (or .weight_g/.weight_v)");
+    const int64_t n0 = v->shape[0], inner = v->numel() / n0;
+    if (g->numel() != n0) return h->fail("bad weight_g shape for " + prefix);
+    *out = *v;
+    for (int64_t i = 0; i < n0; ++i) {
+        double ss = 0;
+        for (int64_t j = 0; j < inner; ++j) ss += (double)v->data[i * inner + j] * v->data[i * inner + j];
+        const float scale = g->data[i] / (float)std::sqrt(ss);
+        for (int64_t j = 0; j < inner; ++j) out->data[i * inner + j] = v->data[i * inner + j] * scale;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Op builders
+// ------------------------------------------------------------------------------------------------
+// causal conv, weight (Cout_total, Cin_g, K)  (layers/conv_layer.py:118-156)
+int make_conv_op(adec_handle* h, Op* op, const std::string& name, const HostTensor& W, const HostTensor* bias,
+                 int stride, int dil, int groups, int pre_act, float slope, bool shared_in) {
+    if (W.shape.size() != 3) return h->fail("conv weight must be 3-D: " + name);
+    const int cout_t = (int)W.shape[0], cin_g = (int)W.shape[1], K = (int)W.shape[2];
+    if (cout_t % groups) return h->fail("Cout not divisible by groups: " + name);
+    const int cout_g = cout_t / groups;
+    op->kind = OP_CONV;
+    op->name = name;
+    op->G = groups;
+    op->pre_act = pre_act;
+    op->slope = slope;
+    op->shared_in = shared_in;
+    op->Cout = round_up(cout_g, 32);
+    if (stride == 1) {
+        op->RG = 1; op->Ktaps = K; op->dil = dil; op->P = (K - 1) * dil; op->down = 1;
+        op->Cin = round_up(cin_g, 32);
+        op->Cin_eff = op->Cin;
+    } else {
+        // k = 2s strided conv (encoder.py:62-68) -> 2-tap conv over s-row groups
+        if (K != 2 * stride || dil != 1) return h->fail(fmt("%s: strided conv needs kernel=2*stride, dilation 1", name.c_str()));
+        if (!is_pow2(cin_g) || cin_g < 4) return h->fail(fmt("%s: strided conv needs power-of-two Cin>=4", name.c_str()));
+        op->RG = stride; op->Ktaps = 2; op->dil = 1; op->P = K - 1; op->down = stride;
+        op->Cin = cin_g;
+        op->Cin_eff = round_up(stride * cin_g, 32);
+    }
+    op->weff.assign((size_t)groups * op->Ktaps * op->Cin_eff * op->Cout, 0.f);
+    for (int g = 0; g < groups; ++g)
+        for (int co = 0; co < cout_g; ++co)
+            for (int ci = 0; ci < cin_g; ++ci)
+                for (int k = 0; k < K; ++k) {
+                    const float v = W.data[((size_t)(g * cout_g + co) * cin_g + ci) * K + k];
+                    int tap, q;
+                    if (stride == 1) { tap = k; q = ci; }
+                    else { tap = k / stride; q = (k % stride) * cin_g + ci; }
+                    op->weff[(((size_t)g * op->Ktaps + tap) * op->Cin_eff + q) * op->Cout + co] = v;
+                }
+    if (bias) {
+        op->hbias.assign((size_t)groups * op->Cout, 0.f);
+        for (int g = 0; g < groups; ++g)
+            for (int co = 0; co < cout_g; ++co) op->hbias[(size_t)g * op->Cout + co] = bias->data[g * cout_g + co];
+    }
+    op->st_groups = shared_in ? 1 : groups;
+    op->st_C = op->st_groups * op->Cin;
+    return 0;
+}
+
+// causal transposed conv, weight (Cin, Cout, 2s)  (layers/conv_layer.py:162-197)
+//   y[j*s+r] = b + W[:,:,r]^T x[j] + W[:,:,s+r]^T x[j-1]      (x[j-1] = tap 0, x[j] = tap 1)
+int make_convtr_op(adec_handle* h, Op* op, const std::string& name, const HostTensor& W, const HostTensor* bias,
+                   int stride, int pre_act, float slope) {
+    if (W.shape.size() != 3 || W.shape[2] != 2 * stride) return h->fail(name + ": transposed conv needs kernel = 2*stride");
+    const int cin = (int)W.shape[0], cout = (int)W.shape[1], K = 2 * stride;
+    op->kind = OP_CONV;
+    op->name = name;
+    op->G = 1; op->RG = 1; op->Ktaps = 2; op->dil = 1; op->P = 1; op->down = 1; op->up = stride;
+    op->pre_act = pre_act; op->slope = slope;
+    op->Cin = round_up(cin, 32);
+    op->Cin_eff = op->Cin;
+    op->Cout = round_up(stride * cout, 32);
+    op->weff.assign((size_t)2 * op->Cin_eff * op->Cout, 0.f);
+    for (int ci = 0; ci < cin; ++ci)
+        for (int co = 0; co < cout; ++co)
+            for (int r = 0; r < stride; ++r) {
+                op->weff[((size_t)0 * op->Cin_eff + ci) * op->Cout + r * cout + co] = W.data[((size_t)ci * cout + co) * K + stride + r];
+                op->weff[((size_t)1 * op->Cin_eff + ci) * op->Cout + r * cout + co] = W.data[((size_t)ci * cout + co) * K + r];
+            }
+    if (bias) {
+        op->hbias.assign(op->Cout, 0.f);
+        for (int r = 0; r < stride; ++r)
+            for (int co = 0; co < cout; ++co) op->hbias[r * cout + co] = bias->data[co];
+    }
+    op->st_groups = 1;
+    op->st_C = op->Cin;
+    return 0;
+}
+
+// residual unit (models/autoencoder/modules/residual_unit.py:49-81): x + W2 * act(conv_k7_dil(act(x)))
+int make_ru_op(adec_handle* h, Op* op, const std::string& name, const HostTensor& W1, const HostTensor& W2, int dil, int act) {
+    if (make_conv_op(h, op, name, W1, nullptr, 1, dil, 1, act, 0.f, false)) return 1;
+    const int c = (int)W1.shape[0];
+    if (W1.shape[1] != c || W2.shape[0] != c || W2.shape[1] != c || W2.shape[2] != 1 || c != op->Cout)
+        return h->fail(name + ": residual unit needs square weights with C % 32 == 0");
+    op->fuse = true;
+    op->mid_act = act;
+    op->weff2.assign((size_t)c * c, 0.f);
+    for (int co = 0; co < c; ++co)
+        for (int ci = 0; ci < c; ++ci) op->weff2[(size_t)ci * c + co] = W2.data[(size_t)co * c + ci];
+    return 0;
+}
+
+int pick_piece_width(const Op& op) {
+    static const int cands[] = {256, 128, 96, 64, 32};
+    for (int cw : cands) {
+        if (op.Cin_eff % cw) continue;
+        if (op.RG > 1 && !(cw % op.Cin == 0 || op.Cin % cw == 0)) continue;
+        return cw;
+    }
+    return 0;
+}
+
+// choose the kernel instantiation, pack + upload weights, allocate state
+int finalize_op(adec_handle* h, Op* op) {
+    if (op->kind != OP_CONV) return 0;
+    int CW, CO;
+    if (op->fuse) {
+        CW = CO = op->Cout;
+    } else {
+        CW = pick_piece_width(*op);
+        CO = op->Cout % 256 == 0 ? 256 : op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
+    }
+    op->kc = CW ? find_conv_kernel(CW, CO, op->fuse) : nullptr;
+    if (!op->kc) return h->fail(fmt("%s: no kernel for Cin_eff=%d Cout=%d fuse=%d", op->name.c_str(), op->Cin_eff, op->Cout, (int)op->fuse));
+    op->n_pieces = op->Cin_eff / CW;
+    op->n_co_tiles = op->Cout / CO;
+    const int KC = op->kc->KC, nkc = CW / KC;
+    op->w_tile_floats = (long long)op->Ktaps * op->Cin_eff * CO;
+    std::vector<float> packed((size_t)op->G * op->n_co_tiles * op->w_tile_floats);
+    size_t o = 0;
+    for (int g = 0; g < op->G; ++g)
+        for (int ct = 0; ct < op->n_co_tiles; ++ct)
+            for (int pc = 0; pc < op->n_pieces; ++pc)
+                for (int tap = 0; tap < op->Ktaps; ++tap)
+                    for (int kcc = 0; kcc < nkc; ++kcc)
+                        for (int k = 0; k < KC; ++k) {
+                            const int q = pc * CW + kcc * KC + k;
+                            const float* src = &op->weff[(((size_t)g * op->Ktaps + tap) * op->Cin_eff + q) * op->Cout + ct * CO];
+                            for (int co = 0; co < CO; ++co) packed[o++] = src[co];
+                        }
+    if (dev_upload(h, &op->w, packed)) return 1;
+    if (op->fuse) {
+        if (dev_upload(h, &op->w2, op->weff2)) return 1;   // [ci][co] == [chunk][kc][co] for CO == C
+    }
+    if (!op->hbias.empty() && dev_upload(h, &op->bias, op->hbias)) return 1;
+    std::vector<float>().swap(op->weff);
+    std::vector<float>().swap(op->weff2);
+    return 0;
+}
+
+int alloc_state(adec_handle* h, Op* op, int n_streams) {
+    const size_t per = (size_t)op->P * op->st_C;
+    if (per == 0) return 0;
+    for (int i = 0; i < 2; ++i) {
+        if (dev_alloc(h, &op->st[i], per * n_streams)) return 1;
+        CK(h, cudaMemset(op->st[i], 0, per * n_streams * sizeof(float)));
+    }
+    op->cur = 0;
+    if (!op->hstate.empty()) {
+        for (int s = 0; s < n_streams; ++s)
+            CK(h, cudaMemcpy(op->st[0] + s * per, op->hstate.data(), per * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// pad_buffer (1, C, P) from the state dict -> (P, st_C) channels-last initial state
+void load_pad_buffer(adec_handle* h, Op* op, const std::string& key, int c_real) {
+    const HostTensor* pb = find(h, key);
+    if (!pb || pb->shape.size() != 3 || op->P == 0) return;
+    const int C = (int)pb->shape[1], P = (int)pb->shape[2];
+    if (P != op->P) return;
+    bool any = false;
+    for (float v : pb->data) any |= (v != 0.f);
+    if (!any) return;
+    op->hstate.assign((size_t)op->P * op->st_C, 0.f);
+    const int groups = op->st_groups, cg = c_real;   // real channels per group
+    for (int g = 0; g < groups; ++g)
+        for (int c = 0; c < cg && g * cg + c < C; ++c)
+            for (int p = 0; p < P; ++p) op->hstate[(size_t)p * op->st_C + g * op->Cin + c] = pb->data[((size_t)(g * cg + c)) * P + p];
+}
+
+// ------------------------------------------------------------------------------------------------
+// plan execution
+// ------------------------------------------------------------------------------------------------
+struct RunCtx {
+    int B;
+    const float* ext_in;
+    float* ext_out;
+    cudaStream_t stream;
+};
+
+int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, int* T_out_final) {
+    // pass 1: workspace sizes
+    size_t need[3] = {0, 0, 0};
+    {
+        int T = T_in;
+        for (const Op& op : ops) {
+            const int Tout = (T - 1) / op.down + 1;
+            if (op.out_buf >= 0) need[op.out_buf] = std::max(need[op.out_buf], (size_t)rc.B * Tout * op.ldy);
+            T = Tout * op.up;
+        }
+    }
+    for (int i = 0; i < 3; ++i)
+        if (need[i] && ensure(h, h->ws[i], need[i])) return 1;
+    if (rc.B != h->n_streams) return h->fail(fmt("batch %d != n_streams %d (call adec_set_streams)", rc.B, h->n_streams));
+
+    int T = T_in;
+    for (Op& op : ops) {
+        const int Tout = (T - 1) / op.down + 1;
+        const float* xin = op.in_buf == BUF_EXT_IN ? rc.ext_in : h->ws[op.in_buf].p;
+        float* yout = op.out_buf == BUF_EXT_OUT ? rc.ext_out : h->ws[op.out_buf].p;
+        const float* st_in = op.st[op.cur];
+        float* st_out = op.st[op.cur ^ 1];
+        cudaError_t e = cudaSuccess;
+        if (op.kind == OP_STEM) {
+            StemArgs a{};
+            a.x = xin; a.x_bs = T; a.st_in = st_in; a.st_out = st_out; a.T = T;
+            a.w = op.w; a.bias = op.bias; a.y = yout; a.y_bs = (long long)T * op.ldy;
+            dim3 grid((T + 1023) / 1024, rc.B);
+            stem_kernel<32, 7><<<grid, 256, 0, rc.stream>>>(a);
+            e = cudaGetLastError();
+        } else if (op.kind == OP_HEAD) {
+            HeadArgs a{};
+            a.x = xin; a.x_bs = (long long)T * op.ldx; a.ldx = op.ldx; a.st_in = st_in; a.st_out = st_out; a.T = T;
+            a.w = op.w; a.bias = op.head_bias; a.pre_act = op.pre_act; a.slope = op.slope; a.post_tanh = op.post_tanh;
+            a.y = yout; a.y_bs = T;
+            dim3 grid((T + 255) / 256, rc.B);
+            head_kernel<32, 7><<<grid, 256, 0, rc.stream>>>(a);
+            e = cudaGetLastError();
+        } else {
+            ConvArgs a{};
+            a.x = xin; a.x_bs = (long long)T * op.ldx; a.ldx = op.ldx; a.x_goff = op.x_goff;
+            a.st_in = st_in; a.st_out = st_out; a.st_ld = op.st_C; a.st_goff = op.shared_in ? 0 : op.Cin; a.st_groups = op.st_groups;
+            a.P = op.P; a.T = T; a.Tout = Tout;
+            a.Ktaps = op.Ktaps; a.dil = op.dil; a.RG = op.RG; a.lgCin = ilog2(op.Cin); a.Cin = op.Cin;
+            a.n_pieces = op.n_pieces; a.pre_act = op.pre_act; a.slope = op.slope; a.mean = op.mean; a.scale = op.scale;
+            a.w = op.w; a.w2 = op.w2; a.bias = op.bias; a.n_co_tiles = op.n_co_tiles; a.Cout_g = op.Cout;
+            a.w_tile_floats = op.w_tile_floats;
+            if (op.fuse) { a.res = xin; a.res_bs = a.x_bs; a.ldr = op.ldx; a.r_goff = 0; }
+            else if (op.res_buf >= 0) { a.res = h->ws[op.res_buf].p; a.res_bs = (long long)Tout * op.ldr; a.ldr = op.ldr; a.r_goff = op.r_goff; }
+            a.y = yout; a.ldy = op.ldy; a.y_goff = op.y_goff; a.out_nct = op.out_nct;
+            a.y_bs = op.out_nct ? (long long)op.G * op.Cout * Tout : (long long)Tout * op.ldy;
+            a.mid_act = op.mid_act;
+            const int TT = op.kc->TT;
+            dim3 grid((Tout + TT - 1) / TT, op.G * op.n_co_tiles, rc.B);
+            e = op.kc->fn(a, grid, TT + (op.Ktaps - 1) * op.dil, rc.stream);
+        }
+        if (e != cudaSuccess) return h->fail(fmt("launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e)));
+        ++h->launches;
+        if (op.P > 0) op.cur ^= 1;
+        T = Tout * op.up;
+    }
+    if (T_out_final) *T_out_final = T;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// model builders
+// ------------------------------------------------------------------------------------------------
+int need_tensor(adec_handle* h, const std::string& key, const HostTensor** out) {
+    *out = find(h, key);
+    if (!*out) return h->fail("missing key " + key);
+    return 0;
+}
+
+int build_stem(adec_handle* h, Op* op, const std::string& prefix, int cout) {
+    const HostTensor* W;
+    if (need_tensor(h, prefix + ".conv.weight", &W)) return 1;
+    if (W->shape[0] != 32 || W->shape[1] != 1 || W->shape[2] != 7 || cout != 32)
+        return h->fail("stem conv: only input_channels=1, encode_channels=32, kernel 7 is built");
+    op->kind = OP_STEM; op->name = prefix; op->P = 6; op->st_C = 1; op->Cin = 1; op->Cout = 32;
+    std::vector<float> w(7 * 32);
+    for (int co = 0; co < 32; ++co)
+        for (int k = 0; k < 7; ++k) w[k * 32 + co] = W->data[co * 7 + k];
+    if (dev_upload(h, &op->w, w)) return 1;
+    if (const HostTensor* b = find(h, prefix + ".conv.bias")) { if (dev_upload(h, &op->bias, b->data)) return 1; }
+    if (const HostTensor* pb = find(h, prefix + ".pad_buffer")) {
+        bool any = false; for (float v : pb->data) any |= v != 0.f;
+        if (any && pb->numel() == 6) op->hstate = pb->data;
+    }
+    return 0;
+}
+
+int build_head(adec_handle* h, Op* op, const std::string& prefix, int pre_act, float slope, bool tanh_out) {
+    HostTensor W;
+    if (get_weight(h, prefix + ".conv", &W)) return 1;
+    if (W.shape[0] != 1 || W.shape[1] != 32 || W.shape[2] != 7)
+        return h->fail("head conv: only 32 -> 1 channels, kernel 7 is built");
+    op->kind = OP_HEAD; op->name = prefix; op->P = 6; op->st_C = 32; op->Cin = 32; op->Cout = 1;
+    op->pre_act = pre_act; op->slope = slope; op->post_tanh = tanh_out;
+    std::vector<float> w(7 * 32);
+    for (int ci = 0; ci < 32; ++ci)
+        for (int k = 0; k < 7; ++k) w[k * 32 + ci] = W.data[ci * 7 + k];
+    if (dev_upload(h, &op->w, w)) return 1;
+    if (const HostTensor* b = find(h, prefix + ".conv.bias")) op->head_bias = b->data[0];
+    op->st_groups = 1;
+    load_pad_buffer(h, op, prefix + ".pad_buffer", 32);
+    return 0;
+}
+
+// wiring helper: ops read `cur` and write another workspace buffer
+struct Wire {
+    int cur = BUF_EXT_IN;
+    int cur_ld = 0;
+    int pick(int avoid1 = -99, int avoid2 = -99) const {
+        for (int i = 0; i < 3; ++i)
+            if (i != cur && i != avoid1 && i != avoid2) return i;
+        return 0;
+    }
+};
+
+void chain(Op* op, Wire* w, int out_ld) {
+    op->in_buf = w->cur; op->ldx = w->cur_ld; op->x_goff = op->shared_in ? 0 : op->Cin;
+    op->out_buf = w->pick(); op->ldy = out_ld; op->y_goff = op->Cout;
+    w->cur = op->out_buf; w->cur_ld = out_ld;
+}
+
+int build_symad(adec_handle* h) {
+    const adec_config& c = h->cfg;
+    if (c.input_channels != 1 || c.output_channels != 1) return h->fail("symAD: only mono (input/output_channels=1) is built");
+    if (c.code_dim != 64) return h->fail("symAD: only code_dim=64 is built");
+    // ---- encoder (models/autoencoder/modules/encoder.py:84-142)
+    Wire w; w.cur = BUF_EXT_IN; w.cur_ld = 1;
+    {
+        Op op;
+        if (build_stem(h, &op, "encoder.conv", c.encode_channels)) return 1;
+        op.in_buf = BUF_EXT_IN; op.ldx = 1; op.out_buf = 0; op.ldy = 32;
+        w.cur = 0; w.cur_ld = 32;
+        h->enc_ops.push_back(std::move(op));
+    }
+    int ch = c.encode_channels;
+    static const int dils[3] = {1, 3, 9};   // encoder.py:33
+    for (int i = 0; i < c.n_enc; ++i) {
+        const std::string pre = fmt("encoder.conv_blocks.%d", i);
+        for (int j = 0; j < 3; ++j) {
+            const std::string ru = pre + fmt(".res_units.%d", j);
+            const HostTensor *W1, *W2;
+            if (need_tensor(h, ru + ".conv1.conv.weight", &W1) || need_tensor(h, ru + ".conv2.weight", &W2)) return 1;
+            Op op;
+            if (make_ru_op(h, &op, ru, *W1, *W2, dils[j], ACT_ELU)) return 1;
+            load_pad_buffer(h, &op, ru + ".conv1.pad_buffer", ch);
+            chain(&op, &w, ch);
+            h->enc_ops.push_back(std::move(op));
+        }
+        const HostTensor* W;
+        if (need_tensor(h, pre + ".conv.conv.weight", &W)) return 1;
+        const HostTensor* b = find(h, pre + ".conv.conv.bias");
+        Op op;
+        if (make_conv_op(h, &op, pre + ".conv", *W, b, c.enc_strides[i], 1, 1, ACT_NONE, 0.f, false)) return 1;
+        load_pad_buffer(h, &op, pre + ".conv.pad_buffer", ch);
+        ch = c.encode_channels * c.enc_ratios[i];
+        chain(&op, &w, ch);
+        h->enc_ops.push_back(std::move(op));
+    }
+    {   // projector (projector.py:40,52-54): k=3, no bias; writes z channels-first (B,64,F)
+        const HostTensor* W;
+        if (need_tensor(h, "projector.project.conv.weight", &W)) return 1;
+        Op op;
+        if (make_conv_op(h, &op, "projector.project", *W, find(h, "projector.project.conv.bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
+        load_pad_buffer(h, &op, "projector.project.pad_buffer", ch);
+        op.in_buf = w.cur; op.ldx = w.cur_ld; op.x_goff = op.Cin;
+        op.out_buf = BUF_EXT_OUT; op.out_nct = true; op.ldy = op.Cout; op.y_goff = op.Cout;
+        if (op.Cout != c.code_dim) return h->fail("projector: code_dim must be a multiple of 32");
+        h->enc_ops.push_back(std::move(op));
+    }
+    // ---- decoder (models/autoencoder/modules/decoder.py:84-148)
+    Wire d; d.cur = BUF_EXT_IN; d.cur_ld = c.code_dim;
+    {
+        const HostTensor* W;
+        if (need_tensor(h, "decoder.conv1.conv.weight", &W)) return 1;
+        Op op;
+        if (make_conv_op(h, &op, "decoder.conv1", *W, find(h, "decoder.conv1.conv.bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
+        load_pad_buffer(h, &op, "decoder.conv1.pad_buffer", c.code_dim);
+        chain(&op, &d, op.Cout);
+        h->dec_ops.push_back(std::move(op));
+    }
+    for (int i = 0; i < c.n_dec; ++i) {
+        const std::string pre = fmt("decoder.conv_blocks.%d", i);
+        const int cin = c.decode_channels * c.dec_ratios[i];
+        const int cout = i < c.n_dec - 1 ? c.decode_channels * c.dec_ratios[i + 1] : c.decode_channels;
+        const HostTensor* W;
+        if (need_tensor(h, pre + ".conv.deconv.weight", &W)) return 1;
+        Op op;
+        if (make_convtr_op(h, &op, pre + ".conv", *W, find(h, pre + ".conv.deconv.bias"), c.dec_strides[i], ACT_NONE, 0.f)) return 1;
+        if (op.Cout != c.dec_strides[i] * cout) return h->fail(pre + ": stride*Cout must be a multiple of 32");
+        load_pad_buffer(h, &op, pre + ".conv.pad_buffer", cin);
+        chain(&op, &d, op.Cout);
+        d.cur_ld = cout;   // (T, s*Cout) is (T*s, Cout)
+        h->dec_ops.push_back(std::move(op));
+        for (int j = 0; j < 3; ++j) {
+            const std::string ru = pre + fmt(".res_units.%d", j);
+            const HostTensor *W1, *W2;
+            if (need_tensor(h, ru + ".conv1.conv.weight", &W1) || need_tensor(h, ru + ".conv2.weight", &W2)) return 1;
+            Op r;
+            if (make_ru_op(h, &r, ru, *W1, *W2, dils[j], ACT_ELU)) return 1;
+            load_pad_buffer(h, &r, ru + ".conv1.pad_buffer", cout);
+            chain(&r, &d, cout);
+            h->dec_ops.push_back(std::move(r));
+        }
+    }
+    {
+        Op op;
+        if (build_head(h, &op, "decoder.conv2", ACT_NONE, 0.f, false)) return 1;
+        op.in_buf = d.cur; op.ldx = d.cur_ld; op.out_buf = BUF_EXT_OUT; op.ldy = 1;
+        h->dec_ops.push_back(std::move(op));
+    }
+    // ---- residual VQ (layers/vq_module.py)
+    const int nq = c.codebook_num, D = c.code_dim, N = c.codebook_size;
+    if (N != 1024) return h->fail("RVQ: only codebook_size=1024 is built");
+    std::vector<float> embed((size_t)nq * D * N), e2((size_t)nq * N), cb((size_t)nq * N * D);
+    for (int i = 0; i < nq; ++i) {
+        const HostTensor* E;
+        if (need_tensor(h, fmt("quantizer.codebook.layers.%d.embed", i), &E)) return 1;
+        if (E->shape.size() != 2 || E->shape[0] != D || E->shape[1] != N) return h->fail("bad embed shape");
+        std::copy(E->data.begin(), E->data.end(), embed.begin() + (size_t)i * D * N);
+        for (int cdx = 0; cdx < N; ++cdx) {
+            // embed.pow(2).sum(0) in torch's order: cascade sum over blocks of 16 rows (see oracle/rvq_oracle.c)
+            float total = 0.f;
+            for (int bk = 0; bk < D; bk += 16) {
+                float part = 0.f;
+                for (int k = bk; k < bk + 16 && k < D; ++k) {
+                    volatile float sq = E->data[(size_t)k * N + cdx] * E->data[(size_t)k * N + cdx];
+                    part = part + sq;
+                }
+                total = bk == 0 ? part : total + part;
+            }
+            e2[(size_t)i * N + cdx] = total;
+            for (int k = 0; k < D; ++k) cb[((size_t)i * N + cdx) * D + k] = E->data[(size_t)k * N + cdx];   // vq_module.py:151-157
+        }
+        find(h, fmt("quantizer.codebook.layers.%d.cluster_size", i));
+        find(h, fmt("quantizer.codebook.layers.%d.embed_avg", i));
+    }
+    if (dev_upload(h, &h->d_embed, embed) || dev_upload(h, &h->d_e2, e2) || dev_upload(h, &h->d_codebook, cb)) return 1;
+    return 0;
+}
+
+int build_hifigan(adec_handle* h) {
+    const adec_config& c = h->cfg;
+    if (c.out_channels != 1) return h->fail("HiFi-GAN: only out_channels=1 is built");
+    if (c.groups < 2) return h->fail("HiFi-GAN: only the MultiGroupConv1d (groups>1, one resblock kernel) variant is built");
+    const float slope = c.negative_slope;
+    if (c.has_stats) {
+        const HostTensor *m, *s;
+        if (need_tensor(h, "mean", &m) || need_tensor(h, "scale", &s)) return 1;
+        std::vector<float> mp(round_up(c.in_channels, 32), 0.f), sp(round_up(c.in_channels, 32), 1.f);
+        std::copy(m->data.begin(), m->data.end(), mp.begin());
+        std::copy(s->data.begin(), s->data.end(), sp.begin());
+        if (dev_upload(h, &h->d_mean, mp) || dev_upload(h, &h->d_scale, sp)) return 1;
+    }
+    Wire w; w.cur = BUF_EXT_IN; w.cur_ld = c.in_channels;
+    {   // input_conv (HiFiGAN.py:84-89, :282-284); decode_norm folded into its window load (:276-279)
+        HostTensor W;
+        if (get_weight(h, "input_conv.conv", &W)) return 1;
+        Op op;
+        if (make_conv_op(h, &op, "input_conv", W, find(h, "input_conv.conv.bias"), 1, 1, 1, c.has_stats ? ACT_NORM : ACT_NONE, 0.f, false)) return 1;
+        op.mean = h->d_mean; op.scale = h->d_scale;
+        load_pad_buffer(h, &op, "input_conv.pad_buffer", c.in_channels);
+        chain(&op, &w, op.Cout);
+        h->dec_ops.push_back(std::move(op));
+    }
+    for (int i = 0; i < c.n_up; ++i) {
+        const int cin = c.channels >> i, cout = c.channels >> (i + 1), s = c.upsample_scales[i];
+        if (c.upsample_kernel_sizes[i] != 2 * s) return h->fail("HiFi-GAN: upsample kernel must be 2*scale (HiFiGAN.py:95)");
+        {
+            HostTensor W;
+            const std::string pre = fmt("upsamples.%d", i);
+            if (get_weight(h, pre + ".deconv", &W)) return 1;
+            Op op;
+            if (make_convtr_op(h, &op, pre, W, find(h, pre + ".deconv.bias"), s, ACT_LRELU, slope)) return 1;
+            if (op.Cout != s * cout) return h->fail(pre + ": scale*Cout must be a multiple of 32");
+            load_pad_buffer(h, &op, pre + ".pad_buffer", cin);
+            chain(&op, &w, op.Cout);
+            w.cur_ld = cout;
+            h->dec_ops.push_back(std::move(op));
+        }
+        // MultiGroupConv1d (multi_fusion.py:82-141): x.repeat folded away (shared_in on the first conv)
+        const int G = c.groups, C3 = G * cout;
+        const int A = w.cur;                 // c (T, cout)
+        const int Bb = w.pick();             // xt
+        const int Cc = w.pick(Bb);           // x (T, 3C)
+        for (int j = 0; j < c.n_dil; ++j) {
+            const std::string p1 = fmt("blocks.%d.convs1.%d", i, j), p2 = fmt("blocks.%d.convs2.%d", i, j);
+            HostTensor W1, W2;
+            if (get_weight(h, p1 + ".conv", &W1) || get_weight(h, p2 + ".conv", &W2)) return 1;
+            Op o1, o2;
+            if (make_conv_op(h, &o1, p1, W1, find(h, p1 + ".conv.bias"), 1, c.resblock_dilations[j], G, ACT_LRELU, slope, j == 0)) return 1;
+            if (make_conv_op(h, &o2, p2, W2, find(h, p2 + ".conv.bias"), 1, 1, G, ACT_LRELU, slope, false)) return 1;
+            if (o1.Cout != cout || o1.Cin != cout) return h->fail(p1 + ": channels must be a multiple of 32");
+            load_pad_buffer(h, &o1, p1 + ".pad_buffer", cout);
+            load_pad_buffer(h, &o2, p2 + ".pad_buffer", cout);
+            o1.in_buf = j == 0 ? A : Cc; o1.ldx = j == 0 ? cout : C3; o1.x_goff = j == 0 ? 0 : cout;
+            o1.out_buf = Bb; o1.ldy = C3; o1.y_goff = cout;
+            o2.in_buf = Bb; o2.ldx = C3; o2.x_goff = cout;
+            o2.res_buf = j == 0 ? A : Cc; o2.ldr = j == 0 ? cout : C3; o2.r_goff = j == 0 ? 0 : cout;
+            o2.out_buf = Cc; o2.ldy = C3; o2.y_goff = cout;     // j>0: in place over the residual (element-wise safe)
+            h->dec_ops.push_back(std::move(o1));
+            h->dec_ops.push_back(std::move(o2));
+        }
+        {
+            HostTensor W;
+            const std::string po = fmt("blocks.%d.conv_out", i);
+            if (get_weight(h, po, &W)) return 1;
+            Op op;
+            if (make_conv_op(h, &op, po, W, find(h, po + ".bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
+            op.in_buf = Cc; op.ldx = C3; op.x_goff = op.Cin;
+            op.out_buf = A; op.ldy = cout; op.y_goff = op.Cout;
+            w.cur = A; w.cur_ld = cout;
+            h->dec_ops.push_back(std::move(op));
+        }
+    }
+    {   // output: LeakyReLU(0.01) -> conv -> tanh (HiFiGAN.py:116-123, :294-296)
+        Op op;
+        if (build_head(h, &op, "output_conv", ACT_LRELU, 0.01f, true)) return 1;
+        op.in_buf = w.cur; op.ldx = w.cur_ld; op.out_buf = BUF_EXT_OUT; op.ldy = 1;
+        h->dec_ops.push_back(std::move(op));
+    }
+    return 0;
+}
+
+int hop_of(const adec_handle* h) {
+    int hop = 1;
+    if (h->cfg.model_type == ADEC_MODEL_SYMAD) for (int i = 0; i < h->cfg.n_enc; ++i) hop *= h->cfg.enc_strides[i];
+    else for (int i = 0; i < h->cfg.n_up; ++i) hop *= h->cfg.upsample_scales[i];
+    return hop;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+}  // namespace
+
+// ==================================================================================================
+// C ABI
+// ==================================================================================================
+extern "C" {
+
+int adec_create(const adec_config* cfg, int device, adec_handle** out) {
+    if (!cfg || !out) { g_create_error = "null argument"; return 1; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        g_create_error = fmt("no usable CUDA device %d (%s); audiodec_b200 has no CPU fallback", device,
+                             e == cudaSuccess ? "out of range" : cudaGetErrorString(e));
+        return 1;
+    }
+    if (cfg->n_enc > ADEC_MAX_STAGES || cfg->n_dec > ADEC_MAX_STAGES || cfg->n_up > ADEC_MAX_STAGES || cfg->n_dil > ADEC_MAX_STAGES) {
+        g_create_error = "too many stages";
+        return 1;
+    }
+    auto* h = new adec_handle();
+    h->cfg = *cfg;
+    h->device = device;
+    DeviceGuard dg(device);
+    if (cudaMalloc((void**)&h->d_err, sizeof(int)) != cudaSuccess || cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) {
+        g_create_error = "cudaMalloc failed";
+        delete h;
+        return 1;
+    }
+    *out = h;
+    return 0;
+}
+
+void adec_destroy(adec_handle* h) {
+    if (!h) return;
+    DeviceGuard dg(h->device);
+    for (void* p : h->owned) cudaFree(p);
+    for (auto& b : h->ws) if (b.p) cudaFree(b.p);
+    for (DevBuf* b : {&h->hx, &h->hz, &h->hzq, &h->hy}) if (b->p) cudaFree(b->p);
+    if (h->hidx) cudaFree(h->hidx);
+    if (h->d_err) cudaFree(h->d_err);
+    delete h;
+}
+
+const char* adec_last_error(const adec_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int adec_set_tensor(adec_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+    if (!h || !key || !data || ndim < 0 || ndim > 4) return h ? h->fail("bad argument to adec_set_tensor") : 1;
+    if (h->finalized) return h->fail("adec_set_tensor after adec_finalize");
+    HostTensor t;
+    t.shape.assign(shape, shape + ndim);
+    t.data.assign(data, data + t.numel());
+    h->tensors[key] = std::move(t);
+    return 0;
+}
+
+int adec_finalize(adec_handle* h) {
+    if (!h) return 1;
+    if (h->finalized) return h->fail("already finalized");
+    DeviceGuard dg(h->device);
+    int rc = h->cfg.model_type == ADEC_MODEL_SYMAD ? build_symad(h)
+           : h->cfg.model_type == ADEC_MODEL_HIFIGAN ? build_hifigan(h)
+           : h->fail("unknown model_type");
+    if (rc) return rc;
+    for (const auto& kv : h->tensors)   // load_state_dict(strict=True): unexpected keys are an error
+        if (!h->consumed.count(kv.first)) return h->fail("unexpected key in state dict: " + kv.first);
+    for (auto* ops : {&h->enc_ops, &h->dec_ops})
+        for (Op& op : *ops) {
+            if (finalize_op(h, &op)) return 1;
+            if (alloc_state(h, &op, 1)) return 1;
+        }
+    h->n_streams = 1;
+    h->tensors.clear();
+    h->finalized = true;
+    return 0;
+}
+
+int adec_n_streams(const adec_handle* h) { return h ? h->n_streams : 0; }
+
+int adec_set_streams(adec_handle* h, int n) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (n == h->n_streams) return 0;
+    if (n < 1) return h->fail("n_streams must be >= 1");
+    if (h->n_streams != 1) return h->fail(fmt("can only expand from 1 stream (have %d); reset or re-create", h->n_streams));
+    DeviceGuard dg(h->device);
+    CK(h, cudaDeviceSynchronize());
+    for (auto* ops : {&h->enc_ops, &h->dec_ops})
+        for (Op& op : *ops) {
+            const size_t per = (size_t)op.P * op.st_C;
+            if (!per) continue;
+            float* nb[2];
+            for (int i = 0; i < 2; ++i) {
+                if (dev_alloc(h, &nb[i], per * n)) return 1;
+            }
+            const long long tot = (long long)per * n;
+            replicate_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(nb[0], op.st[op.cur], (long long)per, n);
+            CK(h, cudaGetLastError());
+            CK(h, cudaMemset(nb[1], 0, per * n * sizeof(float)));
+            op.st[0] = nb[0]; op.st[1] = nb[1]; op.cur = 0;   // old buffers stay in `owned` until destroy
+        }
+    CK(h, cudaDeviceSynchronize());
+    h->n_streams = n;
+    return 0;
+}
+
+int adec_reset(adec_handle* h, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    DeviceGuard dg(h->device);
+    for (auto* ops : {&h->enc_ops, &h->dec_ops})
+        for (Op& op : *ops) {
+            const size_t per = (size_t)op.P * op.st_C;
+            if (!per) continue;
+            for (int i = 0; i < 2; ++i) CK(h, cudaMemsetAsync(op.st[i], 0, per * h->n_streams * sizeof(float), (cudaStream_t)stream));
+        }
+    return 0;
+}
+
+int adec_frames_for(const adec_handle* h, int T) {
+    if (!h || h->cfg.model_type != ADEC_MODEL_SYMAD) return -1;
+    int t = T;
+    for (int i = 0; i < h->cfg.n_enc; ++i) t = (t - 1) / h->cfg.enc_strides[i] + 1;
+    return t;
+}
+
+int adec_hop_length(const adec_handle* h) { return h ? hop_of(h) : -1; }
+
+int adec_encode(adec_handle* h, const float* x, int B, int T, float* z, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail("encode: not a symAD handle");
+    if (B < 1 || T < 1) return h->fail("encode: empty input");
+    DeviceGuard dg(h->device);
+    RunCtx rc{B, x, z, (cudaStream_t)stream};
+    return run_ops(h, h->enc_ops, rc, T, nullptr);
+}
+
+int adec_decode(adec_handle* h, const float* zq, int B, int F, float* y, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (B < 1 || F < 1) return h->fail("decode: empty input");
+    DeviceGuard dg(h->device);
+    RunCtx rc{B, zq, y, (cudaStream_t)stream};
+    return run_ops(h, h->dec_ops, rc, F, nullptr);
+}
+
+int adec_quantize(adec_handle* h, const float* z, int B, int F, int64_t* idx, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail("quantize: not a symAD handle");
+    if (B < 1 || F < 1) return h->fail("quantize: empty input");
+    DeviceGuard dg(h->device);
+    RvqArgs a{};
+    a.z = z; a.B = B; a.F = F; a.nq = h->cfg.codebook_num; a.embed = h->d_embed; a.e2 = h->d_e2; a.idx = (long long*)idx;
+    const long long nfr = (long long)B * F;
+    rvq_kernel<64, 8><<<(unsigned)((nfr + RVQ_FRAMES - 1) / RVQ_FRAMES), RVQ_THREADS, 0, (cudaStream_t)stream>>>(a);
+    CK(h, cudaGetLastError());
+    ++h->launches;
+    return 0;
+}
+
+int adec_lookup(adec_handle* h, const int64_t* idx, int B, int F, float* zq, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail("lookup: not a symAD handle");
+    if (B < 1 || F < 1) return h->fail("lookup: empty input");
+    DeviceGuard dg(h->device);
+    LookupArgs a{};
+    a.idx = (const long long*)idx; a.nfr = (long long)B * F; a.nq = h->cfg.codebook_num; a.D = h->cfg.code_dim;
+    a.codebook = h->d_codebook; a.n_rows = (long long)h->cfg.codebook_num * h->cfg.codebook_size; a.zq = zq; a.err = h->d_err;
+    const long long nth = a.nfr * (a.D / 4);
+    lookup_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
+    CK(h, cudaGetLastError());
+    ++h->launches;
+    return 0;
+}
+
+int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int B, int T, int64_t* idx_host,
+                    float* y_host, void* stream) {
+    if (!enc || !dec) return 1;
+    if (enc->device != dec->device) return enc->fail("codec_host: handles on different devices");
+    DeviceGuard dg(enc->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int F = adec_frames_for(enc, T);
+    if (F < 1) return enc->fail("codec_host: bad T or not a symAD encoder");
+    const int D = enc->cfg.code_dim, nq = enc->cfg.codebook_num, hop = hop_of(dec);
+    if (ensure(enc, enc->hx, (size_t)B * T) || ensure(enc, enc->hz, (size_t)B * D * F) || ensure(enc, enc->hzq, (size_t)B * F * D) ||
+        ensure(enc, enc->hy, (size_t)B * F * hop))
+        return 1;
+    const size_t nidx = (size_t)nq * B * F;
+    if (enc->hidx_cap < nidx) {
+        if (enc->hidx) CK(enc, cudaFree(enc->hidx));
+        CK(enc, cudaMalloc((void**)&enc->hidx, nidx * sizeof(long long)));
+        enc->hidx_cap = nidx;
+    }
+    CK(enc, cudaMemcpyAsync(enc->hx.p, x_host, (size_t)B * T * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (adec_encode(enc, enc->hx.p, B, T, enc->hz.p, stream)) return 1;
+    if (adec_quantize(enc, enc->hz.p, B, F, (int64_t*)enc->hidx, stream)) return 1;
+    if (adec_lookup(enc, (const int64_t*)enc->hidx, B, F, enc->hzq.p, stream)) return 1;
+    if (adec_decode(dec, enc->hzq.p, B, F, enc->hy.p, stream)) { enc->err = dec->err; return 1; }
+    if (idx_host) CK(enc, cudaMemcpyAsync(idx_host, enc->hidx, nidx * sizeof(long long), cudaMemcpyDeviceToHost, s));
+    CK(enc, cudaMemcpyAsync(y_host, enc->hy.p, (size_t)B * F * hop * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CK(enc, cudaStreamSynchronize(s));
+    int herr = 0;
+    CK(enc, cudaMemcpy(&herr, enc->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (herr) return enc->fail("lookup: index out of range");
+    return 0;
+}
+
+int64_t adec_launch_count(const adec_handle* h) { return h ? h->launches : 0; }
+
+// -------------------------------------------------------------------------------------------------
+// single-layer entry points for the unit tests (HOST pointers, reference layouts)
+// -------------------------------------------------------------------------------------------------
+static int run_single(adec_handle* h, Op& op, const float* x, int B, int Cin_real, int T, int groups, int Cout_real_total,
+                      float* state, int P_real, float* y, bool convtr, int stride) {
+    // x (B, Cin_total, T) channels-first -> channels-last with per-group channel padding
+    const int G = op.shared_in ? 1 : op.G;
+    const int cin_g = Cin_real / G, ldx = G * op.Cin;
+    std::vector<float> xl((size_t)B * T * ldx, 0.f);
+    for (int b = 0; b < B; ++b)
+        for (int g = 0; g < G; ++g)
+            for (int c = 0; c < cin_g; ++c)
+                for (int t = 0; t < T; ++t) xl[((size_t)b * T + t) * ldx + g * op.Cin + c] = x[((size_t)b * Cin_real + g * cin_g + c) * T + t];
+    op.hstate.assign((size_t)B * op.P * op.st_C, 0.f);
+    for (int b = 0; b < B; ++b)
+        for (int g = 0; g < G; ++g)
+            for (int c = 0; c < cin_g; ++c)
+                for (int p = 0; p < P_real; ++p)
+                    op.hstate[((size_t)b * op.P + p) * op.st_C + g * op.Cin + c] = state[((size_t)b * Cin_real + g * cin_g + c) * P_real + p];
+    op.in_buf = BUF_EXT_IN; op.ldx = ldx; op.x_goff = op.Cin;
+    op.out_buf = BUF_EXT_OUT; op.ldy = op.G * op.Cout; op.y_goff = op.Cout;
+    if (finalize_op(h, &op)) return 1;
+    const size_t per = (size_t)op.P * op.st_C;
+    for (int i = 0; i < 2; ++i) if (dev_alloc(h, &op.st[i], per * B)) return 1;
+    CK(h, cudaMemcpy(op.st[0], op.hstate.data(), per * B * sizeof(float), cudaMemcpyHostToDevice));
+    h->n_streams = B;
+    const int Tout = (T - 1) / op.down + 1;
+    float *dx, *dy;
+    if (dev_alloc(h, &dx, xl.size()) || dev_alloc(h, &dy, (size_t)B * Tout * op.ldy)) return 1;
+    CK(h, cudaMemcpy(dx, xl.data(), xl.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<Op> ops;
+    ops.push_back(op);
+    RunCtx rc{B, dx, dy, 0};
+    if (run_ops(h, ops, rc, T, nullptr)) return 1;
+    CK(h, cudaDeviceSynchronize());
+    std::vector<float> yl((size_t)B * Tout * op.ldy), sl(per * B);
+    CK(h, cudaMemcpy(yl.data(), dy, yl.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    CK(h, cudaMemcpy(sl.data(), ops[0].st[ops[0].cur], sl.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    if (!convtr) {
+        const int cout_g = Cout_real_total / op.G;
+        for (int b = 0; b < B; ++b)
+            for (int g = 0; g < op.G; ++g)
+                for (int c = 0; c < cout_g; ++c)
+                    for (int t = 0; t < Tout; ++t)
+                        y[((size_t)b * Cout_real_total + g * cout_g + c) * Tout + t] = yl[((size_t)b * Tout + t) * op.ldy + g * op.Cout + c];
+    } else {
+        for (int b = 0; b < B; ++b)
+            for (int c = 0; c < Cout_real_total; ++c)
+                for (int j = 0; j < Tout; ++j)
+                    for (int r = 0; r < stride; ++r)
+                        y[((size_t)b * Cout_real_total + c) * Tout * stride + j * stride + r] = yl[((size_t)b * Tout + j) * op.ldy + r * Cout_real_total + c];
+    }
+    for (int b = 0; b < B; ++b)
+        for (int g = 0; g < G; ++g)
+            for (int c = 0; c < cin_g; ++c)
+                for (int p = 0; p < P_real; ++p)
+                    state[((size_t)b * Cin_real + g * cin_g + c) * P_real + p] = sl[((size_t)b * op.P + p) * op.st_C + g * op.Cin + c];
+    return 0;
+}
+
+int adec_test_causal_conv(int device, const float* x, int B, int Cin, int T, const float* w, const float* bias, int Cout,
+                          int K, int stride, int dil, int groups, int pre_act, float slope, float* state, float* y) {
+    adec_config cfg{};
+    adec_handle* h = nullptr;
+    if (adec_create(&cfg, device, &h)) return 1;
+    DeviceGuard dg(device);
+    HostTensor W, Bt;
+    W.shape = {Cout, Cin / groups, K};
+    W.data.assign(w, w + (size_t)Cout * (Cin / groups) * K);
+    if (bias) { Bt.shape = {Cout}; Bt.data.assign(bias, bias + Cout); }
+    Op op;
+    int rc = make_conv_op(h, &op, "test_conv", W, bias ? &Bt : nullptr, stride, dil, groups, pre_act, slope, false);
+    if (!rc) rc = run_single(h, op, x, B, Cin, T, groups, Cout, state, (K - 1) * dil, y, false, 1);
+    if (rc) g_create_error = h->err;
+    adec_destroy(h);
+    return rc;
+}
+
+int adec_test_causal_convtr(int device, const float* x, int B, int Cin, int T, const float* w, const float* bias, int Cout,
+                            int stride, float* state, float* y) {
+    adec_config cfg{};
+    adec_handle* h = nullptr;
+    if (adec_create(&cfg, device, &h)) return 1;
+    DeviceGuard dg(device);
+    HostTensor W, Bt;
+    W.shape = {Cin, Cout, 2 * stride};
+    W.data.assign(w, w + (size_t)Cin * Cout * 2 * stride);
+    if (bias) { Bt.shape = {Cout}; Bt.data.assign(bias, bias + Cout); }
+    Op op;
+    int rc = make_convtr_op(h, &op, "test_convtr", W, bias ? &Bt : nullptr, stride, ACT_NONE, 0.f);
+    if (!rc) rc = run_single(h, op, x, B, Cin, T, 1, Cout, state, 1, y, true, stride);
+    if (rc) g_create_error = h->err;
+    adec_destroy(h);
+    return rc;
+}
+
+}  // extern "C"

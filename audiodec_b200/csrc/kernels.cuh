@@ -1,0 +1,633 @@
+// audiodec_b200 device kernels (sm_100a).
+//
+// Everything the reference does with torch.cat + nn.Conv1d / nn.ConvTranspose1d + separate
+// activation / add kernels (layers/conv_layer.py:153-156,194-197; residual_unit.py:78-81) is one
+// kernel family here:
+//
+//   conv_gemm_kernel  - stateful causal conv as an im2col-free implicit GEMM on CUDA cores
+//                       (fp32 FFMA: the 1e-4 / bit-identical-index contract rules out TF32/bf16).
+//                       Activations are channels-last (B,T,C) in HBM so a time window is one
+//                       contiguous range and every load is a 128-bit channel vector.  The CTA keeps
+//                       its input window [t0-halo, t0+TT) x C in shared memory (pre-activation and
+//                       causal history applied while it is written), weight tiles are streamed
+//                       L2 -> smem by a producer warp with cp.async.bulk (TMA, 1-D) through a
+//                       4-stage mbarrier ring, 8x8 register micro-tiles accumulate, and the epilogue
+//                       fuses bias / residual / layout.  With FUSE the whole residual unit
+//                       ELU -> k7 dilated -> ELU -> 1x1 -> +x runs without leaving the SM.
+//   stem_kernel       - Cin = 1 first conv (pure store bandwidth).
+//   head_kernel       - Cout = 1 last conv (+ LeakyReLU / bias / tanh for the vocoder).
+//   rvq_kernel        - 8-stage residual VQ: fp32 distances in the reference's rounding order,
+//                       first-index arg-min by warp shuffles, int64 flat indices.
+//   lookup_kernel     - codebook gather-sum.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace adec {
+
+enum PreAct { ACT_NONE = 0, ACT_ELU = 1, ACT_LRELU = 2, ACT_NORM = 3 };
+
+// ------------------------------------------------------------------------------------------------
+// small PTX helpers (mbarrier + 1-D bulk async copy)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        : "=r"(ok)
+        : "r"(smem_u32(b)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+    if (mbar_try_wait(b, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(b, parity)) {
+        if (clock64() - t0 > 8000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float act_elu(float v) { return v > 0.f ? v : expm1f(v); }   // nn.ELU(alpha=1)
+__device__ __forceinline__ float act_lrelu(float v, float s) { return v > 0.f ? v : v * s; }
+
+__device__ __forceinline__ float4 apply_act(float4 v, int act, float slope) {
+    if (act == ACT_ELU) {
+        v.x = act_elu(v.x); v.y = act_elu(v.y); v.z = act_elu(v.z); v.w = act_elu(v.w);
+    } else if (act == ACT_LRELU) {
+        v.x = act_lrelu(v.x, slope); v.y = act_lrelu(v.y, slope); v.z = act_lrelu(v.z, slope); v.w = act_lrelu(v.w, slope);
+    }
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv_gemm_kernel
+// ------------------------------------------------------------------------------------------------
+// The conv is evaluated as  Y[t][co] = sum_{piece,tap,ci} Xw[t + tap*dil][piece*CW + ci] * W[tap][ci][co]
+// over an "extended" input x~ = history(P rows) || chunk(T rows) (layers/conv_layer.py:154).
+//   * stride-s convs (k = 2s) use RG = s: s consecutive x~ rows are folded into one window row of
+//     s*Cin channels, which turns them into 2-tap stride-1 convs (and keeps smem reads conflict-free);
+//   * transposed convs (k = 2s, crop [s:-s], conv_layer.py:197) are 2-tap convs with s*Cout outputs:
+//     y[j*s+r] = b + W[:,:,r]^T x[j] + W[:,:,s+r]^T x[j-1]; the (T, s*Cout) result *is* (T*s, Cout).
+struct ConvArgs {
+    // input activations, channels-last; group g reads channels [g*x_goff, g*x_goff + Cin)
+    const float* x;
+    long long x_bs;
+    int ldx, x_goff;
+    // causal state (history rows), (B, P, st_ld); ping-pong in/out
+    const float* st_in;
+    float* st_out;
+    int st_ld, st_goff, st_groups;   // st_groups: how many groups own distinct state channels
+    int P, T, Tout;
+    int Ktaps, dil, RG, lgCin, Cin;  // Cin: channels per x~ row (per group)
+    int n_pieces;
+    int pre_act;
+    float slope;
+    const float* mean;   // ACT_NORM: (v - mean[c]) / scale[c]   (HiFiGAN.py:276-279)
+    const float* scale;
+    // weights (packed by the host, see pack_weights in adec.cu)
+    const float* w;
+    const float* w2;     // FUSE: the residual unit's 1x1 conv
+    const float* bias;   // [g*Cout_g + co] or nullptr
+    int n_co_tiles, Cout_g;
+    long long w_tile_floats;   // floats per (group, co_tile) of w
+    // residual (raw), output
+    const float* res;
+    long long res_bs;
+    int ldr, r_goff;
+    float* y;
+    long long y_bs;
+    int ldy, y_goff, out_nct;
+    int mid_act;         // FUSE: activation between the two GEMMs
+};
+
+constexpr int CONV_STAGES = 4;
+
+template <int CW, int CO_TILE, int TT, int KC>
+struct ConvCfg {
+    static constexpr int NWC = (CO_TILE / 32) * (TT / 64);   // consumer warps (32 co x 64 t each)
+    static constexpr int NTC = NWC * 32;
+    static constexpr int NTHREADS = NTC + 32;                // + producer warp
+    static constexpr int PITCH = CW + 4;                     // +4 floats: conflict-free float4 row reads
+    static constexpr int CHUNK = KC * CO_TILE;               // floats per weight stage
+    static constexpr size_t smem_bytes(int window_rows) {
+        return 128 + sizeof(float) * ((size_t)CONV_STAGES * CHUNK + (size_t)window_rows * PITCH);
+    }
+};
+
+template <int CO_TILE, int KC, int PITCH>
+__device__ __forceinline__ void mma_chunk(float (&acc)[8][8], const float* __restrict__ xb, const float* __restrict__ wb) {
+#pragma unroll 2
+    for (int kk = 0; kk < KC; kk += 4) {
+        float4 xv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xv[j] = *reinterpret_cast<const float4*>(xb + j * 8 * PITCH + kk);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 wa = *reinterpret_cast<const float4*>(wb + (kk + q) * CO_TILE);
+            const float4 wc = *reinterpret_cast<const float4*>(wb + (kk + q) * CO_TILE + 4);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float xq = q == 0 ? xv[j].x : q == 1 ? xv[j].y : q == 2 ? xv[j].z : xv[j].w;
+                acc[j][0] = fmaf(xq, wa.x, acc[j][0]);
+                acc[j][1] = fmaf(xq, wa.y, acc[j][1]);
+                acc[j][2] = fmaf(xq, wa.z, acc[j][2]);
+                acc[j][3] = fmaf(xq, wa.w, acc[j][3]);
+                acc[j][4] = fmaf(xq, wc.x, acc[j][4]);
+                acc[j][5] = fmaf(xq, wc.y, acc[j][5]);
+                acc[j][6] = fmaf(xq, wc.z, acc[j][6]);
+                acc[j][7] = fmaf(xq, wc.w, acc[j][7]);
+            }
+        }
+    }
+}
+
+template <int CW, int CO_TILE, int TT, int KC, bool FUSE>
+__global__ void __launch_bounds__(ConvCfg<CW, CO_TILE, TT, KC>::NTHREADS)
+conv_gemm_kernel(const ConvArgs a) {
+    using Cfg = ConvCfg<CW, CO_TILE, TT, KC>;
+    constexpr int NWC = Cfg::NWC, NTC = Cfg::NTC, PITCH = Cfg::PITCH, CHUNK = Cfg::CHUNK;
+    constexpr int CO_WARPS = CO_TILE / 32;
+    static_assert(CW % KC == 0 && KC % 4 == 0, "bad KC");
+    static_assert(!FUSE || CW == CO_TILE, "residual-unit fusion needs Cin == Cout == tile");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw);
+    uint64_t* empty = full + CONV_STAGES;
+    float* wst = reinterpret_cast<float*>(smem_raw + 128);
+    float* xs = wst + CONV_STAGES * CHUNK;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int j0 = blockIdx.x * TT;                 // first output row of this tile
+    const int g = blockIdx.y / a.n_co_tiles;
+    const int co_tile = blockIdx.y - g * a.n_co_tiles;
+    const int b = blockIdx.z;
+    const int n1 = a.n_pieces * a.Ktaps * (CW / KC);     // weight chunks of GEMM 1
+    const int ntot = n1 + (FUSE ? CO_TILE / KC : 0);
+
+    if (tid == 0) {
+        for (int s = 0; s < CONV_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NWC);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == NWC) {
+        // ------------------------------ producer warp: stream weight chunks L2 -> smem (TMA 1-D)
+        if (lane == 0) {
+            const float* w1 = a.w + (long long)blockIdx.y * a.w_tile_floats;
+            for (int c = 0; c < ntot; ++c) {
+                const int s = c % CONV_STAGES, it = c / CONV_STAGES;
+                if (it > 0) mbar_wait(&empty[s], (it - 1) & 1);
+                const float* src = (c < n1) ? w1 + (long long)c * CHUNK : a.w2 + (long long)(c - n1) * CHUNK;
+                mbar_arrive_expect_tx(&full[s], CHUNK * 4);
+                bulk_g2s(wst + s * CHUNK, src, CHUNK * 4, &full[s]);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------- consumer warps
+    const int warp_co = warp % CO_WARPS, warp_t = warp / CO_WARPS;
+    const int cg = lane & 3, tg = lane >> 2;
+    const int wrows = TT + (a.Ktaps - 1) * a.dil;   // window rows
+    float acc[8][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+
+    const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
+    const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
+    int c = 0;
+    for (int piece = 0; piece < a.n_pieces; ++piece) {
+        if (piece > 0) named_bar_sync(1, NTC);
+        // ---- window load: x~ rows -> smem, history from state, pre-activation applied once
+        const int nvec = wrows * (CW / 4);
+        for (int idx = tid; idx < nvec; idx += NTC) {
+            const int m = idx / (CW / 4);
+            const int c4 = idx - m * (CW / 4);
+            const int q = piece * CW + c4 * 4;
+            int r = 0, ci = q;
+            if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
+            const long long i = (long long)(j0 + m) * a.RG + r;     // x~ row
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < a.P) {
+                v = *reinterpret_cast<const float4*>(sg + i * a.st_ld + ci);
+            } else {
+                const long long t = i - a.P;
+                if (t < a.T) {
+                    v = __ldg(reinterpret_cast<const float4*>(xg + t * a.ldx + ci));
+                    if (a.pre_act == ACT_NORM) {
+                        const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
+                        const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
+                        v.x = __fdiv_rn(v.x - mu.x, sc.x); v.y = __fdiv_rn(v.y - mu.y, sc.y);
+                        v.z = __fdiv_rn(v.z - mu.z, sc.z); v.w = __fdiv_rn(v.w - mu.w, sc.w);
+                    } else {
+                        v = apply_act(v, a.pre_act, a.slope);
+                    }
+                }
+            }
+            *reinterpret_cast<float4*>(xs + m * PITCH + c4 * 4) = v;
+        }
+        named_bar_sync(1, NTC);
+        // ---- GEMM 1 over (tap, ci-chunk) of this piece
+        for (int tap = 0; tap < a.Ktaps; ++tap) {
+            const float* xrow = xs + (warp_t * 64 + tg + tap * a.dil) * PITCH;
+            for (int kc0 = 0; kc0 < CW; kc0 += KC, ++c) {
+                const int s = c % CONV_STAGES;
+                mbar_wait(&full[s], (c / CONV_STAGES) & 1);
+                mma_chunk<CO_TILE, KC, PITCH>(acc, xrow + kc0, wst + s * CHUNK + warp_co * 32 + cg * 8);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+            }
+        }
+    }
+
+    if (FUSE) {
+        // ---- residual unit: mid = act(conv_k7(act(x))) stays in smem, then the 1x1 conv
+        named_bar_sync(1, NTC);     // everyone is done reading the window
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float* mrow = xs + (warp_t * 64 + tg + 8 * j) * PITCH + warp_co * 32 + cg * 8;
+            float4 v0 = make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+            float4 v1 = make_float4(acc[j][4], acc[j][5], acc[j][6], acc[j][7]);
+            *reinterpret_cast<float4*>(mrow) = apply_act(v0, a.mid_act, a.slope);
+            *reinterpret_cast<float4*>(mrow + 4) = apply_act(v1, a.mid_act, a.slope);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+        }
+        named_bar_sync(1, NTC);
+        const float* xrow = xs + (warp_t * 64 + tg) * PITCH;
+        for (int kc0 = 0; kc0 < CO_TILE; kc0 += KC, ++c) {
+            const int s = c % CONV_STAGES;
+            mbar_wait(&full[s], (c / CONV_STAGES) & 1);
+            mma_chunk<CO_TILE, KC, PITCH>(acc, xrow + kc0, wst + s * CHUNK + warp_co * 32 + cg * 8);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+    }
+
+    // ---------------------------------- epilogue: bias, residual, store
+    {
+        const int co_l = co_tile * CO_TILE + warp_co * 32 + cg * 8;   // channel within the group
+        float bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bv[i] = a.bias ? a.bias[g * a.Cout_g + co_l + i] : 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int t = j0 + warp_t * 64 + tg + 8 * j;
+            if (t >= a.Tout) continue;
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = acc[j][i] + bv[i];
+            if (a.res) {
+                const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
+                const float4 r0 = __ldg(reinterpret_cast<const float4*>(rp));
+                const float4 r1 = __ldg(reinterpret_cast<const float4*>(rp + 4));
+                // x + y  (residual_unit.py:81: `return x + y`)
+                o[0] = r0.x + o[0]; o[1] = r0.y + o[1]; o[2] = r0.z + o[2]; o[3] = r0.w + o[3];
+                o[4] = r1.x + o[4]; o[5] = r1.y + o[5]; o[6] = r1.z + o[6]; o[7] = r1.w + o[7];
+            }
+            if (a.out_nct) {
+                float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) yp[(long long)i * a.Tout] = o[i];
+            } else {
+                float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
+                *reinterpret_cast<float4*>(yp) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(yp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+
+    // ---------------------------------- new causal state = last P rows of x~ (conv_layer.py:155)
+    if (blockIdx.x == gridDim.x - 1 && co_tile == 0 && g < a.st_groups && a.P > 0) {
+        float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
+        const int nvec = a.P * (a.Cin / 4);
+        for (int idx = tid; idx < nvec; idx += NTC) {
+            const int r = idx / (a.Cin / 4);
+            const int ci = (idx - r * (a.Cin / 4)) * 4;
+            const long long i = (long long)a.T + r;      // x~ row
+            float4 v;
+            if (i < a.P) {
+                v = *reinterpret_cast<const float4*>(sg + i * a.st_ld + ci);
+            } else {
+                v = __ldg(reinterpret_cast<const float4*>(xg + (i - a.P) * a.ldx + ci));
+                if (a.pre_act == ACT_NORM) {
+                    const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
+                    const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
+                    v.x = __fdiv_rn(v.x - mu.x, sc.x); v.y = __fdiv_rn(v.y - mu.y, sc.y);
+                    v.z = __fdiv_rn(v.z - mu.z, sc.z); v.w = __fdiv_rn(v.w - mu.w, sc.w);
+                } else {
+                    v = apply_act(v, a.pre_act, a.slope);
+                }
+            }
+            *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + ci) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem: Cin = 1 -> COUT, K taps, stride 1 (encoder.py:106-111).  x (B,T) -> y (B,T,COUT).
+// ------------------------------------------------------------------------------------------------
+struct StemArgs {
+    const float* x; long long x_bs;
+    const float* st_in; float* st_out;   // (B, K-1)
+    int T;
+    const float* w;                      // [K][COUT]
+    const float* bias;                   // [COUT] or nullptr
+    float* y; long long y_bs;
+};
+
+template <int COUT, int K>
+__global__ void __launch_bounds__(256) stem_kernel(const StemArgs a) {
+    constexpr int TT = 1024, P = K - 1, Q = COUT / 4;
+    __shared__ float xw[TT + P];
+    __shared__ __align__(16) float sw[K * COUT];
+    __shared__ __align__(16) float sb[COUT];
+    const int b = blockIdx.y, j0 = blockIdx.x * TT, tid = threadIdx.x;
+    const float* xg = a.x + (long long)b * a.x_bs;
+    for (int i = tid; i < TT + P; i += 256) {
+        const long long r = (long long)j0 + i;       // x~ row
+        float v = 0.f;
+        if (r < P) v = a.st_in[b * P + r];
+        else if (r - P < a.T) v = __ldg(xg + r - P);
+        xw[i] = v;
+    }
+    for (int i = tid; i < K * COUT; i += 256) sw[i] = a.w[i];
+    for (int i = tid; i < COUT; i += 256) sb[i] = a.bias ? a.bias[i] : 0.f;
+    __syncthreads();
+    const int q = tid % Q, tl = tid / Q;
+    constexpr int TSTEP = 256 / Q;
+    float* yg = a.y + (long long)b * a.y_bs;
+    for (int t = tl; t < TT; t += TSTEP) {
+        if (j0 + t >= a.T) break;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float xv = xw[t + k];
+            const float4 w4 = *reinterpret_cast<const float4*>(sw + k * COUT + q * 4);
+            acc.x = fmaf(xv, w4.x, acc.x); acc.y = fmaf(xv, w4.y, acc.y);
+            acc.z = fmaf(xv, w4.z, acc.z); acc.w = fmaf(xv, w4.w, acc.w);
+        }
+        const float4 b4 = *reinterpret_cast<const float4*>(sb + q * 4);
+        acc.x += b4.x; acc.y += b4.y; acc.z += b4.z; acc.w += b4.w;
+        *reinterpret_cast<float4*>(yg + (long long)(j0 + t) * COUT + q * 4) = acc;
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        for (int r = tid; r < P; r += 256) {
+            const long long i = (long long)a.T + r;
+            a.st_out[b * P + r] = (i < P) ? a.st_in[b * P + i] : xg[i - P];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// head: CIN -> 1, K taps (decoder.py:133 / HiFiGAN.py:118-123, :294-296).  x (B,T,CIN) -> y (B,T).
+// ------------------------------------------------------------------------------------------------
+struct HeadArgs {
+    const float* x; long long x_bs; int ldx;
+    const float* st_in; float* st_out;   // (B, K-1, CIN)
+    int T;
+    const float* w;                      // [K][CIN]
+    float bias; int pre_act; float slope; int post_tanh;
+    float* y; long long y_bs;
+};
+
+template <int CIN, int K>
+__global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
+    constexpr int TT = 256, P = K - 1, PITCH = CIN + 4;
+    __shared__ __align__(16) float xs[(TT + P) * PITCH];
+    __shared__ __align__(16) float sw[K * CIN];
+    const int b = blockIdx.y, j0 = blockIdx.x * TT, tid = threadIdx.x;
+    const float* xg = a.x + (long long)b * a.x_bs;
+    const float* sg = a.st_in + (long long)b * P * CIN;
+    for (int idx = tid; idx < (TT + P) * (CIN / 4); idx += 256) {
+        const int m = idx / (CIN / 4), ci = (idx - m * (CIN / 4)) * 4;
+        const long long i = (long long)j0 + m;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < P) v = *reinterpret_cast<const float4*>(sg + i * CIN + ci);
+        else if (i - P < a.T) v = apply_act(__ldg(reinterpret_cast<const float4*>(xg + (i - P) * a.ldx + ci)), a.pre_act, a.slope);
+        *reinterpret_cast<float4*>(xs + m * PITCH + ci) = v;
+    }
+    for (int i = tid; i < K * CIN; i += 256) sw[i] = a.w[i];
+    __syncthreads();
+    const int t = tid;
+    if (j0 + t < a.T) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const float* xr = xs + (t + k) * PITCH;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ci += 4) {
+                const float4 xv = *reinterpret_cast<const float4*>(xr + ci);
+                const float4 wv = *reinterpret_cast<const float4*>(sw + k * CIN + ci);
+                acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
+                acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
+            }
+        }
+        acc += a.bias;
+        if (a.post_tanh) acc = tanhf(acc);
+        a.y[(long long)b * a.y_bs + j0 + t] = acc;
+    }
+    if (blockIdx.x == gridDim.x - 1) {
+        float* so = a.st_out + (long long)b * P * CIN;
+        for (int idx = tid; idx < P * (CIN / 4); idx += 256) {
+            const int r = idx / (CIN / 4), ci = (idx - r * (CIN / 4)) * 4;
+            const long long i = (long long)a.T + r;
+            float4 v;
+            if (i < P) v = *reinterpret_cast<const float4*>(sg + i * CIN + ci);
+            else v = apply_act(__ldg(reinterpret_cast<const float4*>(xg + (i - P) * a.ldx + ci)), a.pre_act, a.slope);
+            *reinterpret_cast<float4*>(so + r * CIN + ci) = v;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual VQ (layers/vq_module.py:90-104,136-149).  Rounding order == oracle/rvq_oracle.c.
+// ------------------------------------------------------------------------------------------------
+struct RvqArgs {
+    const float* z;        // (B, D, F) channels-first (what encode() returns)
+    int B, F, nq;
+    const float* embed;    // (nq, D, N) = state-dict `embed` tensors stacked
+    const float* e2;       // (nq, N)   ||e||^2 in torch's summation order
+    long long* idx;        // (nq, B, F) flat indices (+ N*i)
+};
+
+constexpr int RVQ_FRAMES = 8;     // frames per block
+constexpr int RVQ_THREADS = 128;
+
+template <int D, int NPT>   // codebook size N = RVQ_THREADS * NPT
+__global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
+    constexpr int N = RVQ_THREADS * NPT, FR = RVQ_FRAMES;
+    static_assert(D % 32 == 0, "D must be a multiple of 32");
+    __shared__ float r[FR][D];          // residuals
+    __shared__ float x2[FR];
+    __shared__ float wv[FR][RVQ_THREADS / 32];
+    __shared__ int wi[FR][RVQ_THREADS / 32];
+    __shared__ int best[FR];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long nfr = (long long)a.B * a.F;
+    const long long f0 = (long long)blockIdx.x * FR;
+    for (int i = tid; i < FR * D; i += RVQ_THREADS) {
+        const int f = i / D, k = i - f * D;
+        const long long fr = f0 + f;
+        float v = 0.f;
+        if (fr < nfr) {
+            const long long bb = fr / a.F, ff = fr - bb * a.F;
+            v = a.z[(bb * D + k) * a.F + ff];       // quantizer.py:43 z.transpose(2,1)
+        }
+        r[f][k] = v;
+    }
+    __syncthreads();
+    for (int st = 0; st < a.nq; ++st) {
+        const float* E = a.embed + (long long)st * D * N;
+        // x2 = flatten.pow(2).sum(1): 8-lane vectors, 4 interleaved accumulators, sequential horizontal add
+        if (tid < FR) {
+            float accv[4][8];
+#pragma unroll
+            for (int v = 0; v < 4; ++v)
+#pragma unroll
+                for (int l = 0; l < 8; ++l) accv[v][l] = 0.f;
+#pragma unroll
+            for (int v = 0; v < D / 8; ++v)
+#pragma unroll
+                for (int l = 0; l < 8; ++l) {
+                    const float xv = r[tid][8 * v + l];
+                    accv[v & 3][l] = __fadd_rn(accv[v & 3][l], __fmul_rn(xv, xv));
+                }
+            float s = 0.f;
+#pragma unroll
+            for (int l = 0; l < 8; ++l) {
+                const float t = __fadd_rn(__fadd_rn(__fadd_rn(accv[0][l], accv[1][l]), accv[2][l]), accv[3][l]);
+                s = (l == 0) ? t : __fadd_rn(s, t);
+            }
+            x2[tid] = s;
+        }
+        // dot2[c] = sum_k (2 r_k) * E[k][c], k ascending, fused multiply-add (MKL sgemm order)
+        float acc[FR][NPT];
+#pragma unroll
+        for (int f = 0; f < FR; ++f)
+#pragma unroll
+            for (int m = 0; m < NPT; ++m) acc[f][m] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < D; ++k) {
+            float e[NPT];
+#pragma unroll
+            for (int m = 0; m < NPT; ++m) e[m] = __ldg(E + (long long)k * N + tid + m * RVQ_THREADS);
+#pragma unroll
+            for (int f = 0; f < FR; ++f) {
+                const float rk = 2.0f * r[f][k];
+#pragma unroll
+                for (int m = 0; m < NPT; ++m) acc[f][m] = fmaf(rk, e[m], acc[f][m]);
+            }
+        }
+        __syncthreads();   // x2 visible
+        float e2v[NPT];
+#pragma unroll
+        for (int m = 0; m < NPT; ++m) e2v[m] = __ldg(a.e2 + (long long)st * N + tid + m * RVQ_THREADS);
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            // dist = (x2 - dot2) + e2 ; index = first arg-max of -dist  (vq_module.py:93-98)
+            float bv = 0.f;
+            int bi = 0;
+#pragma unroll
+            for (int m = 0; m < NPT; ++m) {
+                const float nd = -__fadd_rn(__fsub_rn(x2[f], acc[f][m]), e2v[m]);
+                if (m == 0 || nd > bv) { bv = nd; bi = tid + m * RVQ_THREADS; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { wv[f][warp] = bv; wi[f][warp] = bi; }
+        }
+        __syncthreads();
+        if (tid < FR) {
+            float bv = wv[tid][0];
+            int bi = wi[tid][0];
+#pragma unroll
+            for (int w = 1; w < RVQ_THREADS / 32; ++w) {
+                const float ov = wv[tid][w];
+                const int oi = wi[tid][w];
+                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            }
+            best[tid] = bi;
+            const long long fr = f0 + tid;
+            if (fr < nfr) a.idx[(long long)st * nfr + fr] = (long long)bi + (long long)N * st;   // vq_module.py:145-146
+        }
+        __syncthreads();
+        // quantize = x + (e - x); residual -= quantize  (vq_module.py:101-102,143)
+        for (int i = tid; i < FR * D; i += RVQ_THREADS) {
+            const int f = i / D, k = i - f * D;
+            const float rv = r[f][k];
+            const float q = __ldg(E + (long long)k * N + best[f]);
+            const float qq = __fadd_rn(rv, __fsub_rn(q, rv));
+            r[f][k] = __fsub_rn(rv, qq);
+        }
+        __syncthreads();
+    }
+}
+
+// codebook lookup (vq_module.py:159-161): zq[b][f][:] = sum_i codebook[idx[i][b][f]][:], i ascending
+struct LookupArgs {
+    const long long* idx;   // (nq, B*F)
+    long long nfr;
+    int nq, D;
+    const float* codebook;  // (nq*N, D)
+    long long n_rows;       // nq*N (bounds check)
+    float* zq;              // (B*F, D)
+    int* err;               // set to 1 on an out-of-range index
+};
+
+__global__ void __launch_bounds__(256) lookup_kernel(const LookupArgs a) {
+    const int vpf = a.D / 4;    // float4 per frame
+    const long long gid = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (gid >= a.nfr * vpf) return;
+    const long long fr = gid / vpf;
+    const int k4 = (int)(gid - fr * vpf) * 4;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < a.nq; ++i) {
+        const long long row = a.idx[(long long)i * a.nfr + fr];
+        if (row < 0 || row >= a.n_rows) { *a.err = 1; continue; }
+        const float4 v = __ldg(reinterpret_cast<const float4*>(a.codebook + row * a.D + k4));
+        if (i == 0) s = v;
+        else { s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w); }
+    }
+    *reinterpret_cast<float4*>(a.zq + fr * a.D + k4) = s;
+}
+
+// replicate stream 0's state to all streams (adec_set_streams)
+__global__ void replicate_kernel(float* dst, const float* src, long long per_stream, int n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < per_stream * n) dst[i] = src[i % per_stream];
+}
+
+}  // namespace adec

@@ -1,0 +1,126 @@
+/*
+ * audiodec_b200 - C ABI of the B200-native AudioDec streaming forward path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its
+ * plug points are the two abstract hooks AudioCodec._load_encoder / _load_decoder
+ * (bin/stream.py:38-45, implemented in utils/audiodec.py:32-56) whose return values are
+ * duck-typed objects with encode / quantize / lookup / decode / initial_encoder /
+ * initial_decoder / reset_buffer.  Every entry point below replaces one of those
+ * methods; the Python shim in audiodec_b200/codec.py binds them with ctypes and
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C, no torch types; every function returns 0 on success, non-zero on error
+ *     (adec_last_error() gives the message).  Nothing throws, nothing falls back to CPU.
+ *   - all data pointers of the *_dev entry points are DEVICE pointers on the handle's GPU;
+ *     `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - activations are fp32.  Layouts at the boundary are the reference's own
+ *     (SURVEY.md A.3):  x (B,1,T)   z (B,64,F) channels-first   idx (Nq,B,F) int64 flat
+ *     (+1024*i already added)   zq (B,F,64) channels-last   y (B,1,F*hop).
+ *   - a handle owns its weights and its per-stream causal state (the reference's
+ *     pad_buffer tensors, layers/conv_layer.py:144-146,185-187), for `n_streams`
+ *     independent streams.  One handle is driven by one host thread at a time
+ *     (bin/stream.py:343-346); different handles are independent.
+ */
+#ifndef AUDIODEC_B200_H
+#define AUDIODEC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADEC_MAX_STAGES 8
+
+typedef struct adec_handle adec_handle;
+
+enum adec_model_type {
+    ADEC_MODEL_SYMAD = 0,      /* models/autoencoder/AudioDec.py:166 StreamGenerator (codec='audiodec') */
+    ADEC_MODEL_HIFIGAN = 1     /* models/vocoder/HiFiGAN.py:222 StreamGenerator, MultiGroupConv1d fusion (AD v1) */
+};
+
+/* POD mirror of config.yml `generator_params` (exp/.../config.yml:102-134 resp. :102-130). */
+typedef struct adec_config {
+    int model_type;
+    /* symAD (models/autoencoder/AudioDec.py:31-51) */
+    int input_channels, output_channels, encode_channels, decode_channels;
+    int code_dim, codebook_num, codebook_size;
+    int n_enc;  int enc_ratios[ADEC_MAX_STAGES];  int enc_strides[ADEC_MAX_STAGES];
+    int n_dec;  int dec_ratios[ADEC_MAX_STAGES];  int dec_strides[ADEC_MAX_STAGES];
+    int bias;
+    /* HiFi-GAN (models/vocoder/HiFiGAN.py:31-47) */
+    int in_channels, out_channels, channels, kernel_size;
+    int n_up;   int upsample_scales[ADEC_MAX_STAGES];  int upsample_kernel_sizes[ADEC_MAX_STAGES];
+    int resblock_kernel_size;
+    int n_dil;  int resblock_dilations[ADEC_MAX_STAGES];
+    int groups;
+    float negative_slope;
+    int use_weight_norm;
+    int has_stats;
+} adec_config;
+
+/* -- lifetime ---------------------------------------------------------------- */
+/* replaces generator(**config['generator_params']) (utils/audiodec.py:40,54) + .eval().to(dev)
+ * (bin/stream.py:60,69,75).  `device` = CUDA ordinal. */
+int adec_create(const adec_config *cfg, int device, adec_handle **out);
+void adec_destroy(adec_handle *h);
+const char *adec_last_error(const adec_handle *h);   /* h may be NULL: error of the last failed adec_create */
+
+/* -- weight ingest: replaces load_state_dict (utils/audiodec.py:41,55) ------- */
+/* `key` is the reference state-dict key verbatim ("encoder.conv_blocks.0.conv.conv.weight",
+ * "upsamples.1.deconv.weight_g", "quantizer.codebook.layers.3.embed", "mean", ...).  `data` is a HOST
+ * pointer to contiguous fp32 of the given shape.  Unknown keys are an error, except the
+ * training-only buffers cluster_size / embed_avg which are accepted and ignored. */
+int adec_set_tensor(adec_handle *h, const char *key, const float *data, const int64_t *shape, int ndim);
+/* folds weight-norm (w = g*v/||v||, HiFiGAN.py:193-203), repacks weights for the kernels, builds the
+ * flat codebook + ||e||^2 (vq_module.py:151-157,96); errors if any required key is missing (strict=True). */
+int adec_finalize(adec_handle *h);
+
+/* -- per-stream causal state -------------------------------------------------- */
+int adec_n_streams(const adec_handle *h);
+/* n == current: no-op.  current == 1: replicate that stream's state n times.  otherwise error. */
+int adec_set_streams(adec_handle *h, int n_streams);
+/* reset_buffer() (AudioDec.py:250-256, HiFiGAN.py:298-305): zero all history, keep n_streams. */
+int adec_reset(adec_handle *h, void *stream);
+
+/* -- the hot path (device pointers) ------------------------------------------- */
+/* StreamGenerator.encode (AudioDec.py:228-234): x (B,1,T) -> z (B,code_dim,F), F = frames_for(T). */
+int adec_encode(adec_handle *h, const float *x, int B, int T, float *z, void *stream);
+/* StreamGenerator.quantize (AudioDec.py:237-239): z (B,code_dim,F) -> idx (Nq,B,F) int64. Stateless. */
+int adec_quantize(adec_handle *h, const float *z, int B, int F, int64_t *idx, void *stream);
+/* StreamGenerator.lookup (AudioDec.py:242-243): idx (Nq,B,F) -> zq (B,F,code_dim). Stateless. */
+int adec_lookup(adec_handle *h, const int64_t *idx, int B, int F, float *zq, void *stream);
+/* StreamGenerator.decode (AudioDec.py:246-247 / HiFiGAN.py:268-273): zq (B,F,code_dim) -> y (B,1,F*hop). */
+int adec_decode(adec_handle *h, const float *zq, int B, int F, float *y, void *stream);
+
+/* output frames of encode for T input samples: floor((T-1)/s)+1 applied per stride (conv_layer.py:153-156) */
+int adec_frames_for(const adec_handle *h, int T);
+/* product of the strides (utils/audiodec.py:58-62) */
+int adec_hop_length(const adec_handle *h);
+
+/* -- whole path with HOST buffers (what demoFile.py:55-62 does around the four calls) ------- */
+/* x_host (B,1,T) -> idx_host (Nq,B,F) (may be NULL) and y_host (B,1,F*hop).  Copies H2D, runs
+ * enc.encode -> enc.quantize -> enc.lookup -> dec.decode on `stream`, copies D2H and synchronises.
+ * `enc` must be a symAD handle; `dec` a symAD or HiFi-GAN handle (may equal enc). */
+int adec_codec_host(adec_handle *enc, adec_handle *dec, const float *x_host, int B, int T,
+                    int64_t *idx_host, float *y_host, void *stream);
+
+/* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
+int64_t adec_launch_count(const adec_handle *h);
+
+/* -- unit-test entry points for single layers (tests/test_layers_gpu.py) ------- */
+/* One causal conv (layers/conv_layer.py:153-156) on device buffers, channels-first in/out like the
+ * reference: x (B,Cin,T), w (Cout,Cin/groups,K), state (B,Cin,(K-1)*dil) updated in place,
+ * y (B,Cout,floor((T-1)/stride)+1).  bias may be NULL.  pre_act: 0 none, 1 ELU, 2 LeakyReLU(slope). */
+int adec_test_causal_conv(int device, const float *x, int B, int Cin, int T, const float *w, const float *bias,
+                          int Cout, int K, int stride, int dil, int groups, int pre_act, float slope,
+                          float *state, float *y);
+/* One causal transposed conv (layers/conv_layer.py:194-197): w (Cin,Cout,2*stride), state (B,Cin,1). */
+int adec_test_causal_convtr(int device, const float *x, int B, int Cin, int T, const float *w, const float *bias,
+                            int Cout, int stride, float *state, float *y);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUDIODEC_B200_H */

@@ -1,0 +1,78 @@
+"""Single-layer parity on the GPU: the CUDA conv kernels, called through the C ABI test entry points,
+against the known-answer vectors dumped from the reference layer classes
+(layers/conv_layer.py CausalConv1d / CausalConvTranspose1d .inference; tests/golden/layers.npz)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(g, name):
+    return {k.split("/", 1)[1]: g[k] for k in g.files if k.startswith(name + "/")}
+
+
+def _p(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from audiodec_b200 import _lib
+    return _lib.load()
+
+
+@pytest.mark.parametrize("name", ["conv_k7_d3", "conv_k6_s3", "conv_k10_s5_ragged", "conv_k11_d5_g3", "conv_short_chunk"])
+def test_causal_conv_matches_reference(lib, golden_dir, name):
+    from audiodec_b200 import _lib
+    c = _case(np.load(os.path.join(golden_dir, "layers.npz")), name)
+    cin, cout, k, s, d, grp, T = [int(v) for v in c["cfg"]]
+    state = np.zeros((1, cin, (k - 1) * d), np.float32)
+    w, b = np.ascontiguousarray(c["w"]), np.ascontiguousarray(c["b"])
+    for xi, yi in (("x0", "y0"), ("x1", "y1")):      # two consecutive chunks exercise the state carry
+        x = np.ascontiguousarray(c[xi])
+        y = np.zeros_like(c[yi])
+        rc = lib.adec_test_causal_conv(0, _p(x), 1, cin, T, _p(w), _p(b), cout, k, s, d, grp, 0, 0.0, _p(state), _p(y))
+        assert rc == 0, _lib.last_error(None)
+        np.testing.assert_allclose(y, c[yi], atol=2e-5, rtol=0)
+        xx = np.concatenate([np.zeros_like(state) if xi == "x0" else prev, x], -1)
+        np.testing.assert_array_equal(state, xx[:, :, xx.shape[-1] - state.shape[-1]:])   # conv_layer.py:155
+        prev = state.copy()
+
+
+@pytest.mark.parametrize("name", ["convtr_s5", "convtr_s3"])
+def test_causal_convtr_matches_reference(lib, golden_dir, name):
+    from audiodec_b200 import _lib
+    c = _case(np.load(os.path.join(golden_dir, "layers.npz")), name)
+    cin, cout, k, s, _, _, T = [int(v) for v in c["cfg"]]
+    state = np.zeros((1, cin, 1), np.float32)
+    w, b = np.ascontiguousarray(c["w"]), np.ascontiguousarray(c["b"])
+    for xi, yi in (("x0", "y0"), ("x1", "y1")):
+        x = np.ascontiguousarray(c[xi])
+        y = np.zeros_like(c[yi])
+        rc = lib.adec_test_causal_convtr(0, _p(x), 1, cin, T, _p(w), _p(b), cout, s, _p(state), _p(y))
+        assert rc == 0, _lib.last_error(None)
+        np.testing.assert_allclose(y, c[yi], atol=2e-5, rtol=0)
+        np.testing.assert_array_equal(state, x[:, :, -1:])
+
+
+def test_conv_with_preactivation_and_batch(lib):
+    """ELU / LeakyReLU pre-activation + batch of 3 streams against torch fp32 on CPU."""
+    from audiodec_b200 import _lib
+    torch.manual_seed(0)
+    for act, slope in ((1, 0.0), (2, 0.1)):
+        cin, cout, k, d, T, B = 32, 64, 7, 9, 300, 3
+        x = torch.randn(B, cin, T)
+        w = torch.randn(cout, cin, k) / (cin * k) ** 0.5
+        st = torch.randn(B, cin, (k - 1) * d)
+        f = torch.nn.functional.elu if act == 1 else (lambda v: torch.nn.functional.leaky_relu(v, slope))
+        ref = torch.nn.functional.conv1d(torch.cat([st, f(x)], -1), w, None, dilation=d)
+        xn, wn, stn = x.numpy().copy(), w.numpy().copy(), st.numpy().copy()
+        y = np.zeros((B, cout, T), np.float32)
+        rc = lib.adec_test_causal_conv(0, _p(xn), B, cin, T, _p(wn), None, cout, k, 1, d, 1, act, slope, _p(stn), _p(y))
+        assert rc == 0, _lib.last_error(None)
+        np.testing.assert_allclose(y, ref.numpy(), atol=2e-5, rtol=0)
+        np.testing.assert_allclose(stn, torch.cat([st, f(x)], -1)[:, :, -(k - 1) * d:].numpy(), atol=1e-6)

@@ -19,6 +19,7 @@
 
 #include "../../include/audiodec_b200.h"
 #include "kernels.cuh"
+#include "tc_kernels.cuh"
 
 using namespace adec;
 
@@ -90,6 +91,44 @@ const ConvKernelCfg* find_conv_kernel(int CW, int CO, bool fuse) {
     return nullptr;
 }
 
+// tensor-core (tcgen05, 3xTF32) instantiations: NT = output-channel tile, KS = weight-stage K
+template <int NT, int KS, bool F>
+cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kern = tc_conv_kernel<NT, KS, F>;
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
+    kern<<<grid, TC_THREADS, smem_bytes, s>>>(a);
+    return cudaGetLastError();
+}
+
+struct TcKernelCfg { int NT, KS, stages; bool fuse; ConvLaunchFn fn; };
+#define ADEC_TC(NT, KS) \
+    {NT, KS, TcCfg<NT, KS>::STAGES, false, launch_tc<NT, KS, false>}, {NT, KS, TcCfg<NT, KS>::STAGES, true, launch_tc<NT, KS, true>}
+const TcKernelCfg kTcKernels[] = {ADEC_TC(256, 16), ADEC_TC(128, 32), ADEC_TC(64, 32), ADEC_TC(32, 32)};
+
+const TcKernelCfg* find_tc_kernel(int NT, bool fuse) {
+    for (const auto& k : kTcKernels)
+        if (k.NT == NT && k.fuse == fuse) return &k;
+    return nullptr;
+}
+
+float tf32_round_host(float x) {   // cvt.rna.tf32.f32: round to nearest (ties away), 10-bit mantissa
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return x;
+    u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Op: one kernel launch of the plan
 // ------------------------------------------------------------------------------------------------
@@ -114,6 +153,7 @@ struct Op {
     std::vector<float> hstate;  // initial state (P, st_C) or empty (zeros)
     // kernel config
     const ConvKernelCfg* kc = nullptr;
+    const TcKernelCfg* tc = nullptr;   // tensor-core path (default); kc = FFMA path
     int n_pieces = 1, n_co_tiles = 1;
     // device
     float *w = nullptr, *w2 = nullptr, *bias = nullptr;
@@ -144,6 +184,7 @@ struct adec_handle {
     std::set<std::string> consumed;
     std::vector<Op> enc_ops, dec_ops;
     int n_streams = 1;
+    bool use_tc = true;           // ADEC_CONV_PATH=ffma selects the CUDA-core kernels
     DevBuf ws[3];
     std::vector<void*> owned;     // device allocations freed in destroy
     // rvq
@@ -323,8 +364,54 @@ int pick_piece_width(const Op& op) {
 }
 
 // choose the kernel instantiation, pack + upload weights, allocate state
+int finalize_op_tc(adec_handle* h, Op* op) {
+    const int NT = op->Cout % 256 == 0 ? 256 : op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
+    op->tc = find_tc_kernel(NT, op->fuse);
+    if (!op->tc || (op->fuse && NT != op->Cout)) return h->fail(op->name + ": no tensor-core kernel");
+    const int KS = op->tc->KS, CP = TC_CP;
+    op->n_pieces = op->Cin_eff / CP;
+    op->n_co_tiles = op->Cout / NT;
+    op->w_tile_floats = (long long)op->Ktaps * op->Cin_eff * NT * 2;
+    // stage c = ((piece*Ktaps + tap)*(CP/KS) + ks): [hi: (KS/4)][NT][4] | [lo: same]   (UMMA K-major, no swizzle)
+    auto pack = [&](const float* weff, int G, int ntiles, int pieces, int taps, int cin_eff, int cout, std::vector<float>* out) {
+        out->assign((size_t)G * ntiles * taps * cin_eff * NT * 2, 0.f);
+        size_t o = 0;
+        for (int g = 0; g < G; ++g)
+            for (int nt = 0; nt < ntiles; ++nt)
+                for (int pc = 0; pc < pieces; ++pc)
+                    for (int tap = 0; tap < taps; ++tap)
+                        for (int ks = 0; ks < CP / KS; ++ks) {
+                            float* hi = out->data() + o;
+                            float* lo = hi + (size_t)KS * NT;
+                            for (int c4 = 0; c4 < KS / 4; ++c4)
+                                for (int n = 0; n < NT; ++n)
+                                    for (int e = 0; e < 4; ++e) {
+                                        const int k = pc * CP + ks * KS + c4 * 4 + e;
+                                        const float w = weff[(((size_t)g * taps + tap) * cin_eff + k) * cout + nt * NT + n];
+                                        const float wh = tf32_round_host(w);
+                                        hi[((size_t)c4 * NT + n) * 4 + e] = wh;
+                                        lo[((size_t)c4 * NT + n) * 4 + e] = tf32_round_host(w - wh);
+                                    }
+                            o += (size_t)2 * KS * NT;
+                        }
+    };
+    std::vector<float> packed;
+    pack(op->weff.data(), op->G, op->n_co_tiles, op->n_pieces, op->Ktaps, op->Cin_eff, op->Cout, &packed);
+    if (dev_upload(h, &op->w, packed)) return 1;
+    if (op->fuse) {
+        std::vector<float> p2;
+        pack(op->weff2.data(), 1, 1, op->Cout / CP, 1, op->Cout, op->Cout, &p2);
+        if (dev_upload(h, &op->w2, p2)) return 1;
+    }
+    if (!op->hbias.empty() && dev_upload(h, &op->bias, op->hbias)) return 1;
+    std::vector<float>().swap(op->weff);
+    std::vector<float>().swap(op->weff2);
+    return 0;
+}
+
 int finalize_op(adec_handle* h, Op* op) {
     if (op->kind != OP_CONV) return 0;
+    if (h->use_tc) return finalize_op_tc(h, op);
     int CW, CO;
     if (op->fuse) {
         CW = CO = op->Cout;
@@ -453,9 +540,19 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.y = yout; a.ldy = op.ldy; a.y_goff = op.y_goff; a.out_nct = op.out_nct;
             a.y_bs = op.out_nct ? (long long)op.G * op.Cout * Tout : (long long)Tout * op.ldy;
             a.mid_act = op.mid_act;
-            const int TT = op.kc->TT;
-            dim3 grid((Tout + TT - 1) / TT, op.G * op.n_co_tiles, rc.B);
-            e = op.kc->fn(a, grid, TT + (op.Ktaps - 1) * op.dil, rc.stream);
+            if (op.tc) {
+                const int wrows = TC_TT + (op.Ktaps - 1) * op.dil;
+                const int wrp = std::max(wrows, 129) | 1;
+                const int buf1_rows = op.n_pieces > 1 ? wrp : (op.fuse ? 129 : 0);
+                const size_t smem = 256 + sizeof(float) * ((size_t)op.tc->stages * 2 * op.tc->KS * op.tc->NT +
+                                                           (size_t)2 * TC_CP * (wrp + buf1_rows));
+                dim3 grid((Tout + TC_TT - 1) / TC_TT, op.G * op.n_co_tiles, rc.B);
+                e = op.tc->fn(a, grid, (int)smem, rc.stream);
+            } else {
+                const int TT = op.kc->TT;
+                dim3 grid((Tout + TT - 1) / TT, op.G * op.n_co_tiles, rc.B);
+                e = op.kc->fn(a, grid, TT + (op.Ktaps - 1) * op.dil, rc.stream);
+            }
         }
         if (e != cudaSuccess) return h->fail(fmt("launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e)));
         ++h->launches;
@@ -765,6 +862,7 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     auto* h = new adec_handle();
     h->cfg = *cfg;
     h->device = device;
+    if (const char* pth = getenv("ADEC_CONV_PATH")) h->use_tc = strcmp(pth, "ffma") != 0;
     DeviceGuard dg(device);
     if (cudaMalloc((void**)&h->d_err, sizeof(int)) != cudaSuccess || cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed";

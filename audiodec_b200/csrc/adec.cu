@@ -91,27 +91,28 @@ const ConvKernelCfg* find_conv_kernel(int CW, int CO, bool fuse) {
     return nullptr;
 }
 
-// tensor-core (tcgen05, 3xTF32) instantiations: NT = output-channel tile, KS = weight-stage K
-template <int NT, int KS, bool F>
+// tensor-core (tcgen05, 3xTF32) instantiations: NT = output-channel tile (UMMA N)
+template <int NT, bool F>
 cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    auto kern = tc_conv_kernel<NT, KS, F>;
+    auto kern = tc_conv_kernel<NT, F>;
     if (dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
     if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
-    kern<<<grid, TC_THREADS, smem_bytes, s>>>(a);
+    kern<<<grid, TcCfg<NT>::THREADS, smem_bytes, s>>>(a);
     return cudaGetLastError();
 }
 
 struct TcKernelCfg { int NT, KS, stages; bool fuse; ConvLaunchFn fn; };
-#define ADEC_TC(NT, KS) \
-    {NT, KS, TcCfg<NT, KS>::STAGES, false, launch_tc<NT, KS, false>}, {NT, KS, TcCfg<NT, KS>::STAGES, true, launch_tc<NT, KS, true>}
-const TcKernelCfg kTcKernels[] = {ADEC_TC(256, 16), ADEC_TC(128, 32), ADEC_TC(64, 32), ADEC_TC(32, 32)};
+#define ADEC_TC(NT) \
+    {NT, TC_CP, TcCfg<NT>::STAGES, false, launch_tc<NT, false>}, {NT, TC_CP, TcCfg<NT>::STAGES, true, launch_tc<NT, true>}
+const TcKernelCfg kTcKernels[] = {ADEC_TC(128), ADEC_TC(64), ADEC_TC(32)};
+constexpr int kTcMaxFuse = 128;    // residual units wider than this run as two launches on the tensor-core path
 
 const TcKernelCfg* find_tc_kernel(int NT, bool fuse) {
     for (const auto& k : kTcKernels)
@@ -353,6 +354,22 @@ int make_ru_op(adec_handle* h, Op* op, const std::string& name, const HostTensor
     return 0;
 }
 
+// Tensor-core path, C > 128: the fused unit would need 2*C > 256 accumulator registers per drain thread, so it runs
+// as two launches: k7 dilated conv (ELU on load) -> mid, then 1x1 conv (ELU on load) + skip.
+void split_ru_op(const Op& ru, Op* conv, Op* pw) {
+    *conv = ru;
+    conv->fuse = false;
+    conv->weff2.clear();
+    conv->mid_act = ACT_NONE;
+    *pw = Op();
+    pw->kind = OP_CONV;
+    pw->name = ru.name + ".conv2";
+    pw->G = 1; pw->Cin = ru.Cout; pw->Cin_eff = ru.Cout; pw->Cout = ru.Cout; pw->Ktaps = 1; pw->dil = 1; pw->RG = 1; pw->P = 0;
+    pw->pre_act = ru.mid_act; pw->slope = ru.slope;
+    pw->weff = ru.weff2;            // [ci][co] == [1 tap][Cin_eff][Cout]
+    pw->st_groups = 1; pw->st_C = ru.Cout;
+}
+
 int pick_piece_width(const Op& op) {
     static const int cands[] = {256, 128, 96, 64, 32};
     for (int cw : cands) {
@@ -365,7 +382,7 @@ int pick_piece_width(const Op& op) {
 
 // choose the kernel instantiation, pack + upload weights, allocate state
 int finalize_op_tc(adec_handle* h, Op* op) {
-    const int NT = op->Cout % 256 == 0 ? 256 : op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
+    const int NT = op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
     op->tc = find_tc_kernel(NT, op->fuse);
     if (!op->tc || (op->fuse && NT != op->Cout)) return h->fail(op->name + ": no tensor-core kernel");
     const int KS = op->tc->KS, CP = TC_CP;
@@ -624,6 +641,31 @@ void chain(Op* op, Wire* w, int out_ld) {
     w->cur = op->out_buf; w->cur_ld = out_ld;
 }
 
+// append a residual unit to `ops`: one fused launch, or (tensor-core path, C > 128) conv + 1x1 launches
+int push_ru(adec_handle* h, std::vector<Op>* ops, Wire* w, const std::string& ru, int dil, int ch) {
+    const HostTensor *W1, *W2;
+    if (need_tensor(h, ru + ".conv1.conv.weight", &W1) || need_tensor(h, ru + ".conv2.weight", &W2)) return 1;
+    Op op;
+    if (make_ru_op(h, &op, ru, *W1, *W2, dil, ACT_ELU)) return 1;
+    load_pad_buffer(h, &op, ru + ".conv1.pad_buffer", ch);
+    if (h->use_tc && op.Cout > kTcMaxFuse) {
+        Op conv, pw;
+        split_ru_op(op, &conv, &pw);
+        const int x_buf = w->cur;
+        chain(&conv, w, ch);
+        pw.in_buf = w->cur; pw.ldx = ch; pw.x_goff = pw.Cin;
+        pw.res_buf = x_buf; pw.ldr = ch; pw.r_goff = 0;
+        pw.out_buf = w->pick(x_buf); pw.ldy = ch; pw.y_goff = pw.Cout;
+        w->cur = pw.out_buf; w->cur_ld = ch;
+        ops->push_back(std::move(conv));
+        ops->push_back(std::move(pw));
+    } else {
+        chain(&op, w, ch);
+        ops->push_back(std::move(op));
+    }
+    return 0;
+}
+
 int build_symad(adec_handle* h) {
     const adec_config& c = h->cfg;
     if (c.input_channels != 1 || c.output_channels != 1) return h->fail("symAD: only mono (input/output_channels=1) is built");
@@ -641,16 +683,8 @@ int build_symad(adec_handle* h) {
     static const int dils[3] = {1, 3, 9};   // encoder.py:33
     for (int i = 0; i < c.n_enc; ++i) {
         const std::string pre = fmt("encoder.conv_blocks.%d", i);
-        for (int j = 0; j < 3; ++j) {
-            const std::string ru = pre + fmt(".res_units.%d", j);
-            const HostTensor *W1, *W2;
-            if (need_tensor(h, ru + ".conv1.conv.weight", &W1) || need_tensor(h, ru + ".conv2.weight", &W2)) return 1;
-            Op op;
-            if (make_ru_op(h, &op, ru, *W1, *W2, dils[j], ACT_ELU)) return 1;
-            load_pad_buffer(h, &op, ru + ".conv1.pad_buffer", ch);
-            chain(&op, &w, ch);
-            h->enc_ops.push_back(std::move(op));
-        }
+        for (int j = 0; j < 3; ++j)
+            if (push_ru(h, &h->enc_ops, &w, pre + fmt(".res_units.%d", j), dils[j], ch)) return 1;
         const HostTensor* W;
         if (need_tensor(h, pre + ".conv.conv.weight", &W)) return 1;
         const HostTensor* b = find(h, pre + ".conv.conv.bias");
@@ -696,16 +730,8 @@ int build_symad(adec_handle* h) {
         chain(&op, &d, op.Cout);
         d.cur_ld = cout;   // (T, s*Cout) is (T*s, Cout)
         h->dec_ops.push_back(std::move(op));
-        for (int j = 0; j < 3; ++j) {
-            const std::string ru = pre + fmt(".res_units.%d", j);
-            const HostTensor *W1, *W2;
-            if (need_tensor(h, ru + ".conv1.conv.weight", &W1) || need_tensor(h, ru + ".conv2.weight", &W2)) return 1;
-            Op r;
-            if (make_ru_op(h, &r, ru, *W1, *W2, dils[j], ACT_ELU)) return 1;
-            load_pad_buffer(h, &r, ru + ".conv1.pad_buffer", cout);
-            chain(&r, &d, cout);
-            h->dec_ops.push_back(std::move(r));
-        }
+        for (int j = 0; j < 3; ++j)
+            if (push_ru(h, &h->dec_ops, &d, pre + fmt(".res_units.%d", j), dils[j], cout)) return 1;
     }
     {
         Op op;
@@ -1119,6 +1145,26 @@ int adec_test_causal_conv(int device, const float* x, int B, int Cin, int T, con
     Op op;
     int rc = make_conv_op(h, &op, "test_conv", W, bias ? &Bt : nullptr, stride, dil, groups, pre_act, slope, false);
     if (!rc) rc = run_single(h, op, x, B, Cin, T, groups, Cout, state, (K - 1) * dil, y, false, 1);
+    if (rc) g_create_error = h->err;
+    adec_destroy(h);
+    return rc;
+}
+
+int adec_test_residual_unit(int device, const float* x, int B, int C, int T, const float* w1, const float* w2, int K, int dil,
+                            float* state, float* y) {
+    adec_config cfg{};
+    adec_handle* h = nullptr;
+    if (adec_create(&cfg, device, &h)) return 1;
+    DeviceGuard dg(device);
+    HostTensor W1, W2;
+    W1.shape = {C, C, K};
+    W1.data.assign(w1, w1 + (size_t)C * C * K);
+    W2.shape = {C, C, 1};
+    W2.data.assign(w2, w2 + (size_t)C * C);
+    Op op;
+    int rc = make_ru_op(h, &op, "test_ru", W1, W2, dil, ACT_ELU);
+    if (!rc && h->use_tc && op.Cout > kTcMaxFuse) rc = h->fail("test_ru: C > 128 runs as two ops on the tensor-core path; test those separately");
+    if (!rc) rc = run_single(h, op, x, B, C, T, 1, C, state, (K - 1) * dil, y, false, 1);
     if (rc) g_create_error = h->err;
     adec_destroy(h);
     return rc;

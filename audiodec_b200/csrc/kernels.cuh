@@ -22,6 +22,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace adec {
 
@@ -52,11 +53,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(b, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(b, parity)) {
-        if (clock64() - t0 > 8000000000LL) __trap();
+        if (clock64() - t0 > 4000000000LL) {
+            printf("adec: mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x, blockIdx.y,
+                   blockIdx.z, threadIdx.x);
+            __trap();
+        }
     }
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {

@@ -7,16 +7,21 @@
 //     LBO = ROWS*16 B).  In this layout a conv tap is a *row-shifted start address* of the same
 //     window - no im2col, no copies: tap k of a dilated conv reads rows [k*dil, k*dil+128).
 //   * precision: 3xTF32 error-compensated products (a = a_hi + a_lo, w = w_hi + w_lo in tf32;
-//     acc += a_lo*w_hi + a_hi*w_lo + a_hi*w_hi, fp32 accumulation in TMEM).  Measured max error
-//     ~1e-7 relative (tools/tc_probe.cu) - fp32-grade, which the bit-identical-index contract needs;
-//     plain TF32 (2e-3) is not.
-//   * warp roles: warp 0 = weight producer (cp.async.bulk / TMA 1-D, host-pre-split hi|lo tiles already in
-//     UMMA layout) + TMEM allocator; warp 1 = MMA issuer (one thread); warps 2-5 = activation producers
-//     (global -> pre-activation -> hi/lo split -> smem, 32-channel pieces, double buffered) and then the
-//     epilogue (tcgen05.ld, bias / residual, stores).  mbarrier rings connect them; tcgen05.commit
-//     releases smem back to the producers.
-//   * FUSE: the residual unit keeps acc1 in TMEM, the producers turn it into the activated hi/lo operand of
-//     the 1x1 conv piece by piece, acc2 is a second TMEM region; the skip tensor is added in the epilogue.
+//     a_lo*w_hi + a_hi*w_lo + a_hi*w_hi).  The TMEM accumulator rounds toward zero at every MMA
+//     (measured, tools/tc_probe2.cu: -1.7e-8..-3.8e-8 relative per accumulation step), which over the
+//     hundreds of steps of a long-K conv becomes a 1e-5-level systematic shrink - enough to flip
+//     nearest-codeword decisions.  So accumulation is GROUPED: one (32-channel piece, tap) = 12 MMAs
+//     (8 small-term MMAs first, then 4 main ones) goes into a fresh TMEM partial, and the drain warps
+//     add the partials into fp32 REGISTER accumulators with round-to-nearest adds.  Residual bias
+//     ~1e-7 per conv, same order as the FFMA path's rounding noise.
+//   * warp roles (384 or 512 threads): warp 0 = weight producer (cp.async.bulk / TMA 1-D; host-pre-split
+//     hi|lo tiles already in UMMA layout) + TMEM allocator; warp 1 = MMA issuer (elect-one, uniform
+//     datapath); warps 4-7 = activation producers (global -> pre-activation -> hi/lo split -> smem,
+//     32-channel pieces, double buffered); warps 8+ = drain / epilogue (tcgen05.ld partials, register
+//     accumulation, bias / residual, stores).  mbarrier rings connect them; tcgen05.commit releases smem
+//     stages and signals partials.
+//   * FUSE (C <= 128): the residual unit's activated intermediate goes from the drain warps' registers
+//     straight back to smem as the hi/lo operand of the 1x1 conv; the skip tensor is added in the epilogue.
 #pragma once
 #include "kernels.cuh"
 
@@ -40,72 +45,77 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred P1;\n elect.sync _|P1, 0xffffffff;\n selp.u32 %0, 1, 0, P1;\n}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ float tf32_rna(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
-    uint32_t r[32];
+// 32 lanes x 16 columns of fp32 from TMEM (lane quarter of this warp), no wait
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
     asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 constexpr int TC_TT = 128;        // output rows per CTA (UMMA M)
-constexpr int TC_CP = 32;         // channels per activation piece
-constexpr int TC_THREADS = 192;   // warp0 TMA+alloc, warp1 MMA, warps 2-5 producers/epilogue
-constexpr int TC_NPROD = 128;
+constexpr int TC_CP = 32;         // channels per activation piece == K of one weight stage
+constexpr int TC_MIDP = 129;      // row pitch (rows) of the 1x1 conv's activated operand (odd)
 
-template <int NT, int KS>
+template <int NT>
 struct TcCfg {
-    static constexpr int STAGES = NT == 256 ? 3 : (NT == 128 ? 3 : 4);
-    static constexpr int B_STAGE_FLOATS = 2 * KS * NT;                      // hi | lo
+    static constexpr int STAGES = NT == 128 ? 3 : 4;
+    static constexpr int B_STAGE_FLOATS = 2 * TC_CP * NT;                   // hi | lo
+    static constexpr int NDG = NT == 128 ? 2 : 1;                           // drain warpgroups (each owns NT/NDG columns)
+    static constexpr int THREADS = 256 + 128 * NDG;                         // warps 0-3 control, 4-7 producers, 8+ drain
+    static constexpr int NCOL = NT / NDG;                                   // accumulator registers per drain thread
 };
 
-template <int NT, int KS, bool FUSE>
-__global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const ConvArgs a) {
-    using Cfg = TcCfg<NT, KS>;
-    constexpr int S = Cfg::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT;
-    constexpr int KS_PER_PIECE = CP / KS;
-    static_assert(CP % KS == 0 && KS % 8 == 0, "bad KS");
+template <int NT, bool FUSE>
+__global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const ConvArgs a) {
+    using Cfg = TcCfg<NT>;
+    constexpr int S = Cfg::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG, NCOL = Cfg::NCOL;
+    constexpr int MIDP = TC_MIDP;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    constexpr uint32_t TMEM_COLS = FUSE ? 2 * NT : NT;
-    constexpr int MIDP = 129;   // row pitch (rows) of the 1x1 conv's activated operand
+    constexpr uint32_t TMEM_COLS = 2 * NT;      // two partial-accumulator buffers
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);     // [S]
-    uint64_t* b_empty = b_full + S;                                // [S]
-    uint64_t* a_full = b_empty + S;                                // [2]
-    uint64_t* a_empty = a_full + 2;                                // [2]
-    uint64_t* acc_full = a_empty + 2;                              // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 2);
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);     // [S]  weights landed
+    uint64_t* b_empty = b_full + S;                                // [S]  weights consumed
+    uint64_t* a_full = b_empty + S;                                // [2]  activation piece written
+    uint64_t* a_empty = a_full + 2;                                // [2]  activation piece consumed
+    uint64_t* p_full = a_empty + 2;                                // [2]  TMEM partial complete
+    uint64_t* p_empty = p_full + 2;                                // [2]  TMEM partial drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
     float* bst = reinterpret_cast<float*>(smem_raw + 256);
     const int wrows = TT + (a.Ktaps - 1) * a.dil;
     const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
     float* abuf0 = bst + S * BST;
     float* abuf1 = abuf0 + 2 * CP * wrp;
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);       // warp-uniform for the compiler
     const int j0 = blockIdx.x * TT;
     const int g = blockIdx.y / a.n_co_tiles;
     const int co_tile = blockIdx.y - g * a.n_co_tiles;
     const int b = blockIdx.z;
-    const int n_k1 = a.n_pieces * a.Ktaps * KS_PER_PIECE;
-    const int n_k2 = FUSE ? (NT / CP) * KS_PER_PIECE : 0;
+    const int n_g1 = a.n_pieces * a.Ktaps;                          // groups (= weight stages) of GEMM 1
+    const int n_g2 = FUSE ? NT / CP : 0;                            // groups of the fused 1x1 conv
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&a_full[i], TC_NPROD); mbar_init(&a_empty[i], 1); mbar_init(&acc_full[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
+            mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG);
+        }
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -121,72 +131,71 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const ConvArgs a) {
         // ------------------------------------------------ weight producer (TMA 1-D bulk copies)
         if (lane == 0) {
             const float* w1 = a.w + (long long)blockIdx.y * a.w_tile_floats;
-            for (int c = 0; c < n_k1 + n_k2; ++c) {
+            for (int c = 0; c < n_g1 + n_g2; ++c) {
                 const int s = c % S, it = c / S;
-                if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1);
-                const float* src = c < n_k1 ? w1 + (long long)c * BST : a.w2 + (long long)(c - n_k1) * BST;
+                if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1, 100 + c);
+                const float* src = c < n_g1 ? w1 + (long long)c * BST : a.w2 + (long long)(c - n_g1) * BST;
                 mbar_arrive_expect_tx(&b_full[s], BST * 4);
                 bulk_g2s(bst + s * BST, src, BST * 4, &b_full[s]);
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer (one thread)
-        if (lane == 0) {
-            int c = 0, gp = 0;
-            const uint32_t a_lbo = (uint32_t)wrp * 16u, b_lbo = (uint32_t)NT * 16u;
-            for (int phase = 0; phase < (FUSE ? 2 : 1); ++phase) {
-                const int pieces = phase == 0 ? a.n_pieces : NT / CP;
-                const int taps = phase == 0 ? a.Ktaps : 1;
-                const uint32_t lbo = phase == 0 ? a_lbo : (uint32_t)MIDP * 16u;
-                const uint32_t acc = tmem + (phase == 0 ? 0 : NT);
-                uint32_t accumulate = 0;
-                for (int p = 0; p < pieces; ++p, ++gp) {
-                    const int buf = gp & 1;
-                    mbar_wait(&a_full[buf], (gp >> 1) & 1);
+        // ------------------------------------------------ MMA issuer: whole warp runs the loop (uniform), one lane issues
+        int c = 0, gp = 0;
+        const uint32_t b_lbo = (uint32_t)NT * 16u;
+        const uint32_t abuf0_u = smem_u32(abuf0), abuf1_u = smem_u32(abuf1), bst_u = smem_u32(bst);
+        for (int phase = 0; phase < (FUSE ? 2 : 1); ++phase) {
+            const int pieces = phase == 0 ? a.n_pieces : NT / CP;
+            const int taps = phase == 0 ? a.Ktaps : 1;
+            const uint32_t lbo = (uint32_t)(phase == 0 ? wrp : MIDP) * 16u;
+            for (int p = 0; p < pieces; ++p, ++gp) {
+                const int buf = gp & 1;
+                mbar_wait(&a_full[buf], (gp >> 1) & 1, 200 + gp);
+                const uint32_t a_hi = buf ? abuf1_u : abuf0_u;
+                const uint32_t a_lo = a_hi + (uint32_t)(CP / 4) * lbo;     // lo block follows the hi block
+                for (int tap = 0; tap < taps; ++tap, ++c) {
+                    const int s = c % S, pb = c & 1;
+                    mbar_wait(&b_full[s], (c / S) & 1, 300 + c);
+                    if (c >= 2) mbar_wait(&p_empty[pb], ((c >> 1) - 1) & 1, 400 + c);
                     tc_fence_after();
-                    const uint32_t a_hi = smem_u32(buf ? abuf1 : abuf0);
-                    const uint32_t a_lo = a_hi + (uint32_t)(CP / 4) * lbo;     // lo block follows the hi block
-                    for (int tap = 0; tap < taps; ++tap) {
-                        const uint32_t row_off = (uint32_t)(tap * a.dil) * 16u;
-                        for (int ks = 0; ks < KS_PER_PIECE; ++ks, ++c) {
-                            const int s = c % S;
-                            mbar_wait(&b_full[s], (c / S) & 1);
-                            tc_fence_after();
-                            const uint32_t b_hi = smem_u32(bst + s * BST);
-                            const uint32_t b_lo = b_hi + (uint32_t)KS * NT * 4u;
+                    const uint32_t row_off = (uint32_t)(tap * a.dil) * 16u;
+                    const uint32_t b_hi = bst_u + (uint32_t)s * (BST * 4u);
+                    const uint32_t b_lo = b_hi + (uint32_t)CP * NT * 4u;
+                    const uint32_t acc = tmem + (uint32_t)pb * NT;
+                    if (elect_one()) {
+                        // small terms first (the partial is still tiny while they accumulate), then the main products
 #pragma unroll
-                            for (int k8 = 0; k8 < KS / 8; ++k8) {
-                                const uint32_t ao = (uint32_t)((ks * KS) / 4 + k8 * 2) * lbo + row_off;
-                                const uint32_t bo = (uint32_t)(k8 * 2) * b_lbo;
-                                const uint64_t dah = umma_desc(a_hi + ao, lbo), dal = umma_desc(a_lo + ao, lbo);
-                                const uint64_t dbh = umma_desc(b_hi + bo, b_lbo), dbl = umma_desc(b_lo + bo, b_lbo);
-                                umma_tf32(acc, dal, dbh, IDESC, accumulate);   // small terms first
-                                umma_tf32(acc, dah, dbl, IDESC, 1u);
-                                umma_tf32(acc, dah, dbh, IDESC, 1u);
-                                accumulate = 1u;
-                            }
-                            umma_commit(&b_empty[s]);       // weights stage free once these MMAs retire
-                        }
+                        for (int k8 = 0; k8 < CP / 8; ++k8)
+                            umma_tf32(acc, umma_desc(a_lo + (uint32_t)(k8 * 2) * lbo + row_off, lbo),
+                                      umma_desc(b_hi + (uint32_t)(k8 * 2) * b_lbo, b_lbo), IDESC, k8 ? 1u : 0u);
+#pragma unroll
+                        for (int k8 = 0; k8 < CP / 8; ++k8)
+                            umma_tf32(acc, umma_desc(a_hi + (uint32_t)(k8 * 2) * lbo + row_off, lbo),
+                                      umma_desc(b_lo + (uint32_t)(k8 * 2) * b_lbo, b_lbo), IDESC, 1u);
+#pragma unroll
+                        for (int k8 = 0; k8 < CP / 8; ++k8)
+                            umma_tf32(acc, umma_desc(a_hi + (uint32_t)(k8 * 2) * lbo + row_off, lbo),
+                                      umma_desc(b_hi + (uint32_t)(k8 * 2) * b_lbo, b_lbo), IDESC, 1u);
+                        umma_commit(&b_empty[s]);       // weight stage free once these MMAs retire
+                        umma_commit(&p_full[pb]);       // partial ready for the drain warps
+                        if (tap == taps - 1) umma_commit(&a_empty[buf]);   // activation piece free
                     }
-                    umma_commit(&a_empty[buf]);             // activation piece free
+                    __syncwarp();
                 }
-                umma_commit(&acc_full[phase]);              // accumulator complete
             }
         }
-    } else {
-        // ------------------------------------------------ activation producers, then epilogue (128 threads)
-        const int pt = tid - 64;                            // 0..127
-        const int row = (warp & 3) * 32 + lane;             // TMEM lane == output row this thread owns
+    } else if (warp >= 4 && warp < 8) {
+        // ------------------------------------------------ activation producers (128 threads)
+        const int pt = tid - 128;
         const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
         const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
-        int gp = 0;
-        for (int p = 0; p < a.n_pieces; ++p, ++gp) {
-            const int buf = gp & 1;
-            if (gp >= 2) mbar_wait(&a_empty[buf], ((gp >> 1) - 1) & 1);
+        for (int p = 0; p < a.n_pieces; ++p) {
+            const int buf = p & 1;
+            if (p >= 2) mbar_wait(&a_empty[buf], ((p >> 1) - 1) & 1, 500 + p);
             float* hi = buf ? abuf1 : abuf0;
             float* lo = hi + CP * wrp;
             const int nvec = wrows * (CP / 4);
-            for (int idx = pt; idx < nvec; idx += TC_NPROD) {
+            for (int idx = pt; idx < nvec; idx += 128) {
                 const int m = idx >> 3, c4 = idx & 7;
                 const int q = p * CP + c4 * 4;
                 int r = 0, ci = q;
@@ -217,70 +226,11 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const ConvArgs a) {
             fence_async_smem();
             mbar_arrive(&a_full[buf]);
         }
-        if (FUSE) {
-            // mid = act(acc1) -> hi/lo operand of the 1x1 conv, 32 columns (one piece) at a time
-            mbar_wait(&acc_full[0], 0);
-            tc_fence_after();
-            for (int p = 0; p < NT / CP; ++p, ++gp) {
-                const int buf = gp & 1;
-                if (gp >= 2) mbar_wait(&a_empty[buf], ((gp >> 1) - 1) & 1);
-                float* hi = buf ? abuf1 : abuf0;
-                float* lo = hi + CP * MIDP;
-                float v[32];
-                tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + p * CP, v);
-#pragma unroll
-                for (int c4 = 0; c4 < 8; ++c4) {
-                    float4 m4 = apply_act(make_float4(v[c4 * 4], v[c4 * 4 + 1], v[c4 * 4 + 2], v[c4 * 4 + 3]), a.mid_act, a.slope);
-                    const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
-                    const float4 l = make_float4(tf32_rna(m4.x - h.x), tf32_rna(m4.y - h.y), tf32_rna(m4.z - h.z), tf32_rna(m4.w - h.w));
-                    *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
-                    *reinterpret_cast<float4*>(lo + (c4 * MIDP + row) * 4) = l;
-                }
-                tc_fence_before();
-                fence_async_smem();
-                mbar_arrive(&a_full[buf]);
-            }
-        }
-        mbar_wait(&acc_full[FUSE ? 1 : 0], 0);
-        tc_fence_after();
-        // ---- epilogue: this thread owns output row `row` (time step j0 + row), all NT channels of the tile
-        const int t = j0 + row;
-        const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (FUSE ? NT : 0);
-        for (int c0 = 0; c0 < NT; c0 += 32) {
-            float v[32];
-            tmem_ld32(tacc + c0, v);            // .sync.aligned: executed by the whole warp, also for rows past Tout
-            if (t < a.Tout) {
-                const int co_l = co_tile * NT + c0;
-                if (a.bias) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] += __ldg(a.bias + g * a.Cout_g + co_l + i);
-                }
-                if (a.res) {
-                    const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp) + i);
-                        v[4 * i] = r4.x + v[4 * i]; v[4 * i + 1] = r4.y + v[4 * i + 1];
-                        v[4 * i + 2] = r4.z + v[4 * i + 2]; v[4 * i + 3] = r4.w + v[4 * i + 3];
-                    }
-                }
-                if (a.out_nct) {
-                    float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) yp[(long long)i * a.Tout] = v[i];
-                } else {
-                    float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        *(reinterpret_cast<float4*>(yp) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                }
-            }
-        }
-        // ---- new causal state (conv_layer.py:155)
+        // ---- new causal state (conv_layer.py:155), independent of the MMA pipeline
         if (blockIdx.x == gridDim.x - 1 && co_tile == 0 && g < a.st_groups && a.P > 0) {
             float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
             const int nvec = a.P * (a.Cin / 4);
-            for (int idx = pt; idx < nvec; idx += TC_NPROD) {
+            for (int idx = pt; idx < nvec; idx += 128) {
                 const int r = idx / (a.Cin / 4);
                 const int ci = (idx - r * (a.Cin / 4)) * 4;
                 const long long i = (long long)a.T + r;
@@ -299,6 +249,94 @@ __global__ void __launch_bounds__(TC_THREADS) tc_conv_kernel(const ConvArgs a) {
                     }
                 }
                 *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + ci) = v;
+            }
+        }
+    } else if (warp >= 8) {
+        // ------------------------------------------------ drain warps: register accumulation, mid conversion, epilogue
+        const int dg = (warp - 8) >> 2;                     // drain group: owns columns [dg*NCOL, (dg+1)*NCOL)
+        const int row = (warp & 3) * 32 + lane;             // TMEM lane == output row of this thread
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        float racc[NCOL];
+#pragma unroll
+        for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+        int c = 0;
+        auto drain = [&](int ngroups) {
+            for (int gi = 0; gi < ngroups; ++gi, ++c) {
+                const int pb = c & 1;
+                mbar_wait(&p_full[pb], (c >> 1) & 1, 600 + c);
+                tc_fence_after();
+                const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)dg * NCOL;
+#pragma unroll
+                for (int c0 = 0; c0 < NCOL; c0 += 32) {
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(taddr + c0, r0);
+                    tmem_ld16(taddr + c0 + 16, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        racc[c0 + i] = __fadd_rn(racc[c0 + i], __uint_as_float(r0[i]));
+                        racc[c0 + 16 + i] = __fadd_rn(racc[c0 + 16 + i], __uint_as_float(r1[i]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&p_empty[pb]);
+            }
+        };
+        drain(n_g1);
+        if (FUSE) {
+            // mid = act(conv_k7(act(x))) -> hi/lo operand of the 1x1 conv, written straight from registers
+            // Piece gq re-uses the buffer of piece gq-2, i.e. needs completion #((gq>>1)-1) of a_empty[buf].  A parity
+            // wait is unambiguous here because completion #((gq>>1)-2) (piece gq-4) retired long before GEMM 1's last
+            // partial, which these threads have already drained.
+#pragma unroll
+            for (int pl = 0; pl < NCOL / CP; ++pl) {
+                const int p = dg * (NCOL / CP) + pl;        // piece index in MMA consumption order
+                const int gq = a.n_pieces + p, buf = gq & 1;
+                if (gq >= 2) mbar_wait(&a_empty[buf], ((gq >> 1) - 1) & 1, 700 + gq);
+                float* hi = buf ? abuf1 : abuf0;
+                float* lo = hi + CP * MIDP;
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const float4 m4 = apply_act(make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1], racc[pl * CP + c4 * 4 + 2],
+                                                            racc[pl * CP + c4 * 4 + 3]), a.mid_act, a.slope);
+                    const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
+                    const float4 l = make_float4(tf32_rna(m4.x - h.x), tf32_rna(m4.y - h.y), tf32_rna(m4.z - h.z), tf32_rna(m4.w - h.w));
+                    *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
+                    *reinterpret_cast<float4*>(lo + (c4 * MIDP + row) * 4) = l;
+                }
+                fence_async_smem();
+                mbar_arrive(&a_full[buf]);
+            }
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+            drain(n_g2);
+        }
+        // ---- epilogue: this thread owns output row `row` (time step j0 + row), NCOL channels
+        const int t = j0 + row;
+        if (t < a.Tout) {
+            const int co_l = co_tile * NT + dg * NCOL;          // channel within the group
+            if (a.bias) {
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) racc[i] += __ldg(a.bias + g * a.Cout_g + co_l + i);
+            }
+            if (a.res) {
+                const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
+#pragma unroll
+                for (int i = 0; i < NCOL / 4; ++i) {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                    racc[4 * i] = r4.x + racc[4 * i]; racc[4 * i + 1] = r4.y + racc[4 * i + 1];
+                    racc[4 * i + 2] = r4.z + racc[4 * i + 2]; racc[4 * i + 3] = r4.w + racc[4 * i + 3];
+                }
+            }
+            if (a.out_nct) {
+                float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) yp[(long long)i * a.Tout] = racc[i];
+            } else {
+                float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
+#pragma unroll
+                for (int i = 0; i < NCOL / 4; ++i)
+                    *(reinterpret_cast<float4*>(yp) + i) = make_float4(racc[4 * i], racc[4 * i + 1], racc[4 * i + 2], racc[4 * i + 3]);
             }
         }
     }

@@ -111,7 +111,7 @@ int64_t adec_launch_count(const adec_handle *h);
 
 /* -- unit-test entry points for single layers (tests/test_layers_gpu.py) ------- */
 /* One causal conv (layers/conv_layer.py:153-156) on device buffers, channels-first in/out like the
- * reference: x (B,Cin,T), w (Cout,Cin/groups,K), state (B,Cin,(K-1)*dil) updated in place,
+ * reference: x (B,Cin,T) HOST pointers, w (Cout,Cin/groups,K), state (B,Cin,(K-1)*dil) updated in place,
  * y (B,Cout,floor((T-1)/stride)+1).  bias may be NULL.  pre_act: 0 none, 1 ELU, 2 LeakyReLU(slope). */
 int adec_test_causal_conv(int device, const float *x, int B, int Cin, int T, const float *w, const float *bias,
                           int Cout, int K, int stride, int dil, int groups, int pre_act, float slope,
@@ -119,6 +119,11 @@ int adec_test_causal_conv(int device, const float *x, int B, int Cin, int T, con
 /* One causal transposed conv (layers/conv_layer.py:194-197): w (Cin,Cout,2*stride), state (B,Cin,1). */
 int adec_test_causal_convtr(int device, const float *x, int B, int Cin, int T, const float *w, const float *bias,
                             int Cout, int stride, float *state, float *y);
+
+/* One causal residual unit (models/autoencoder/modules/residual_unit.py:49-81):
+ * y = x + W2 * ELU(conv_k7_dil(ELU(x))); x,y (B,C,T), w1 (C,C,K), w2 (C,C,1), state (B,C,(K-1)*dil). */
+int adec_test_residual_unit(int device, const float *x, int B, int C, int T, const float *w1, const float *w2,
+                            int K, int dil, float *state, float *y);
 
 #ifdef __cplusplus
 }

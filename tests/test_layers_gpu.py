@@ -76,3 +76,45 @@ def test_conv_with_preactivation_and_batch(lib):
         assert rc == 0, _lib.last_error(None)
         np.testing.assert_allclose(y, ref.numpy(), atol=2e-5, rtol=0)
         np.testing.assert_allclose(stn, torch.cat([st, f(x)], -1)[:, :, -(k - 1) * d:].numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("C,d,T,B", [(32, 1, 700, 2), (64, 3, 300, 1), (64, 9, 130, 2), (128, 9, 260, 1)])
+def test_residual_unit_fused(lib, C, d, T, B):
+    """Fused residual unit (residual_unit.py:78-81) against torch fp32 on CPU, two consecutive chunks."""
+    from audiodec_b200 import _lib
+    torch.manual_seed(C + d)
+    w1 = torch.randn(C, C, 7) * 1.2 / (7 * C) ** 0.5
+    w2 = torch.randn(C, C, 1) * 0.6 / C ** 0.5
+    st = torch.zeros(B, C, 6 * d)
+    stn = st.numpy().copy()
+    for _ in range(2):
+        x = torch.randn(B, C, T)
+        xx = torch.cat([st, torch.nn.functional.elu(x)], -1)
+        st = xx[:, :, -6 * d:]
+        mid = torch.nn.functional.conv1d(xx, w1, None, dilation=d)
+        ref = x + torch.nn.functional.conv1d(torch.nn.functional.elu(mid), w2)
+        y = np.zeros((B, C, T), np.float32)
+        rc = lib.adec_test_residual_unit(0, _p(x.numpy().copy()), B, C, T, _p(w1.numpy().copy()), _p(w2.numpy().copy()), 7, d, _p(stn), _p(y))
+        assert rc == 0, _lib.last_error(None)
+        np.testing.assert_allclose(y, ref.numpy(), atol=5e-6, rtol=0)
+        np.testing.assert_allclose(stn, st.numpy(), atol=1e-6)
+
+
+@pytest.mark.parametrize("cin,cout,k,s,d", [(128, 256, 7, 1, 1), (256, 128, 3, 1, 1), (64, 128, 8, 4, 1), (256, 512, 10, 5, 1), (512, 64, 3, 1, 1)])
+def test_wide_convs_multi_piece(lib, cin, cout, k, s, d):
+    """Convs whose input is wider than one 32-channel piece / one output tile, vs torch fp32 CPU (tight tolerance:
+    this is the check that the tensor-core path is fp32-grade, not TF32-grade)."""
+    from audiodec_b200 import _lib
+    torch.manual_seed(cin + cout)
+    T, B = 310, 2
+    x = torch.randn(B, cin, T)
+    w = torch.randn(cout, cin, k) / (cin * k) ** 0.5
+    bias = torch.randn(cout) * 0.1
+    st = torch.randn(B, cin, (k - 1) * d)
+    ref = torch.nn.functional.conv1d(torch.cat([st, x], -1), w, bias, stride=s, dilation=d)
+    stn = st.numpy().copy()
+    y = np.zeros(tuple(ref.shape), np.float32)
+    rc = lib.adec_test_causal_conv(0, _p(x.numpy().copy()), B, cin, T, _p(w.numpy().copy()), _p(bias.numpy().copy()), cout, k, s, d, 1, 0, 0.0,
+                                   _p(stn), _p(y))
+    assert rc == 0, _lib.last_error(None)
+    np.testing.assert_allclose(y, ref.numpy(), atol=3e-6, rtol=0)

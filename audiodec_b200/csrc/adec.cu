@@ -98,8 +98,13 @@ cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t
     int dev = 0;
     cudaGetDevice(&dev);
     auto kern = tc_conv_kernel<NT, F>;
+#ifdef ADEC_TIMELINE
+    constexpr int kMaxDyn = 227 * 1024 - 2048;   // room for the static timeline buffer
+#else
+    constexpr int kMaxDyn = 227 * 1024;
+#endif
     if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }

@@ -72,17 +72,21 @@ constexpr int TC_MIDP = 129;      // row pitch (rows) of the 1x1 conv's activate
 
 template <int NT>
 struct TcCfg {
-    static constexpr int STAGES = NT == 128 ? 3 : 4;
+    static constexpr int STAGES = NT == 64 ? 4 : 3;
+    static constexpr int MIN_CTAS = NT == 32 ? 2 : 1;                       // co-resident CTAs hide each other's serial phases
     static constexpr int B_STAGE_FLOATS = 2 * TC_CP * NT;                   // hi | lo
     static constexpr int NDG = NT == 128 ? 2 : 1;                           // drain warpgroups (each owns NT/NDG columns)
-    static constexpr int THREADS = 256 + 128 * NDG;                         // warps 0-3 control, 4-7 producers, 8+ drain
+    static constexpr int NPROD = NT == 128 ? 128 : 256;                     // activation-producer threads
+    static constexpr int DRAIN0 = (128 + NPROD) / 32;                       // first drain warp
+    static constexpr int THREADS = 128 + NPROD + 128 * NDG;                 // warps 0-3 control, then producers, then drain
     static constexpr int NCOL = NT / NDG;                                   // accumulator registers per drain thread
 };
 
 template <int NT, bool FUSE>
-__global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const ConvArgs a) {
+__global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_conv_kernel(const ConvArgs a) {
     using Cfg = TcCfg<NT>;
     constexpr int S = Cfg::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG, NCOL = Cfg::NCOL;
+    constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0;
     constexpr int MIDP = TC_MIDP;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t TMEM_COLS = 2 * NT;      // two partial-accumulator buffers
@@ -113,7 +117,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], 128); mbar_init(&a_empty[i], 1);
+            mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 1);
             mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG);
         }
         mbar_fence_init();
@@ -126,6 +130,13 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+#ifdef ADEC_TIMELINE
+    __shared__ unsigned tl_[6][64];
+    const long long tl0_ = clock64();
+#define TL(role, i) do { if ((i) < 64) tl_[role][(i)] = (unsigned)(clock64() - tl0_); } while (0)
+#else
+#define TL(role, i) do { } while (0)
+#endif
 
     if (warp == 0) {
         // ------------------------------------------------ weight producer (TMA 1-D bulk copies)
@@ -137,6 +148,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                 const float* src = c < n_g1 ? w1 + (long long)c * BST : a.w2 + (long long)(c - n_g1) * BST;
                 mbar_arrive_expect_tx(&b_full[s], BST * 4);
                 bulk_g2s(bst + s * BST, src, BST * 4, &b_full[s]);
+                TL(0, c);
             }
         }
     } else if (warp == 1) {
@@ -158,6 +170,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                     mbar_wait(&b_full[s], (c / S) & 1, 300 + c);
                     if (c >= 2) mbar_wait(&p_empty[pb], ((c >> 1) - 1) & 1, 400 + c);
                     tc_fence_after();
+                    if (lane == 0) TL(1, c);
                     const uint32_t row_off = (uint32_t)(tap * a.dil) * 16u;
                     const uint32_t b_hi = bst_u + (uint32_t)s * (BST * 4u);
                     const uint32_t b_lo = b_hi + (uint32_t)CP * NT * 4u;
@@ -179,13 +192,14 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                         umma_commit(&b_empty[s]);       // weight stage free once these MMAs retire
                         umma_commit(&p_full[pb]);       // partial ready for the drain warps
                         if (tap == taps - 1) umma_commit(&a_empty[buf]);   // activation piece free
+                        TL(2, c);
                     }
                     __syncwarp();
                 }
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ------------------------------------------------ activation producers (128 threads)
+    } else if (warp >= 4 && warp < DRAIN0) {
+        // ------------------------------------------------ activation producers (NPROD threads)
         const int pt = tid - 128;
         const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
         const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
@@ -194,43 +208,61 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
             if (p >= 2) mbar_wait(&a_empty[buf], ((p >> 1) - 1) & 1, 500 + p);
             float* hi = buf ? abuf1 : abuf0;
             float* lo = hi + CP * wrp;
-            const int nvec = wrows * (CP / 4);
-            for (int idx = pt; idx < nvec; idx += 128) {
-                const int m = idx >> 3, c4 = idx & 7;
-                const int q = p * CP + c4 * 4;
-                int r = 0, ci = q;
-                if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
-                const long long i = (long long)(j0 + m) * a.RG + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < a.P) {
-                    v = *reinterpret_cast<const float4*>(sg + i * a.st_ld + ci);
-                } else {
-                    const long long t = i - a.P;
-                    if (t < a.T) {
-                        v = __ldg(reinterpret_cast<const float4*>(xg + t * a.ldx + ci));
-                        if (a.pre_act == ACT_NORM) {
-                            const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
-                            const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
-                            v.x = __fdiv_rn(v.x - mu.x, sc.x); v.y = __fdiv_rn(v.y - mu.y, sc.y);
-                            v.z = __fdiv_rn(v.z - mu.z, sc.z); v.w = __fdiv_rn(v.w - mu.w, sc.w);
-                        } else {
-                            v = apply_act(v, a.pre_act, a.slope);
-                        }
+            // thread -> fixed 4-channel column c4 and rows m0, m0+RPP, ...: all index math is loop-invariant
+            constexpr int RPP = NPROD / 8;               // rows per pass
+            constexpr int UNR = 6;                       // loads in flight per thread (memory-level parallelism)
+            const int c4 = pt & 7, m0 = pt >> 3;
+            const int q = p * CP + c4 * 4;
+            int r = 0, ci = q;
+            if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
+            const float* srow = sg + ci;
+            const float* xrow = xg + ci;
+            float* hcol = hi + (c4 * wrp) * 4;
+            float* lcol = lo + (c4 * wrp) * 4;
+            for (int mb = m0; mb < wrows; mb += RPP * UNR) {
+                float4 v[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int m = mb + u * RPP;
+                    const long long i = (long long)(j0 + m) * a.RG + r;
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (m < wrows) {
+                        if (i < a.P) v[u] = *reinterpret_cast<const float4*>(srow + i * a.st_ld);
+                        else if (i - a.P < a.T) v[u] = __ldg(reinterpret_cast<const float4*>(xrow + (i - a.P) * a.ldx));
                     }
                 }
-                const float4 h = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-                const float4 l = make_float4(tf32_rna(v.x - h.x), tf32_rna(v.y - h.y), tf32_rna(v.z - h.z), tf32_rna(v.w - h.w));
-                *reinterpret_cast<float4*>(hi + (c4 * wrp + m) * 4) = h;
-                *reinterpret_cast<float4*>(lo + (c4 * wrp + m) * 4) = l;
+#pragma unroll
+                for (int u = 0; u < UNR; ++u) {
+                    const int m = mb + u * RPP;
+                    if (m < wrows) {
+                        const long long i = (long long)(j0 + m) * a.RG + r;
+                        float4 x4 = v[u];
+                        if (i >= a.P && i - a.P < a.T) {        // chunk rows get the pre-activation; history rows already have it
+                            if (a.pre_act == ACT_NORM) {
+                                const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
+                                const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
+                                x4.x = __fdiv_rn(x4.x - mu.x, sc.x); x4.y = __fdiv_rn(x4.y - mu.y, sc.y);
+                                x4.z = __fdiv_rn(x4.z - mu.z, sc.z); x4.w = __fdiv_rn(x4.w - mu.w, sc.w);
+                            } else {
+                                x4 = apply_act(x4, a.pre_act, a.slope);
+                            }
+                        }
+                        const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
+                        const float4 l = make_float4(tf32_rna(x4.x - h.x), tf32_rna(x4.y - h.y), tf32_rna(x4.z - h.z), tf32_rna(x4.w - h.w));
+                        *reinterpret_cast<float4*>(hcol + m * 4) = h;
+                        *reinterpret_cast<float4*>(lcol + m * 4) = l;
+                    }
+                }
             }
             fence_async_smem();
             mbar_arrive(&a_full[buf]);
+            if (pt == 0) TL(3, p);
         }
         // ---- new causal state (conv_layer.py:155), independent of the MMA pipeline
         if (blockIdx.x == gridDim.x - 1 && co_tile == 0 && g < a.st_groups && a.P > 0) {
             float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
             const int nvec = a.P * (a.Cin / 4);
-            for (int idx = pt; idx < nvec; idx += 128) {
+            for (int idx = pt; idx < nvec; idx += NPROD) {
                 const int r = idx / (a.Cin / 4);
                 const int ci = (idx - r * (a.Cin / 4)) * 4;
                 const long long i = (long long)a.T + r;
@@ -251,9 +283,9 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                 *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + ci) = v;
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= DRAIN0) {
         // ------------------------------------------------ drain warps: register accumulation, mid conversion, epilogue
-        const int dg = (warp - 8) >> 2;                     // drain group: owns columns [dg*NCOL, (dg+1)*NCOL)
+        const int dg = (warp - DRAIN0) >> 2;                     // drain group: owns columns [dg*NCOL, (dg+1)*NCOL)
         const int row = (warp & 3) * 32 + lane;             // TMEM lane == output row of this thread
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         float racc[NCOL];
@@ -265,6 +297,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                 const int pb = c & 1;
                 mbar_wait(&p_full[pb], (c >> 1) & 1, 600 + c);
                 tc_fence_after();
+                if (tid == DRAIN0 * 32) TL(4, c);
                 const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)dg * NCOL;
 #pragma unroll
                 for (int c0 = 0; c0 < NCOL; c0 += 32) {
@@ -280,6 +313,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                 }
                 tc_fence_before();
                 mbar_arrive(&p_empty[pb]);
+                if (tid == DRAIN0 * 32) TL(5, c);
             }
         };
         drain(n_g1);
@@ -305,7 +339,8 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
                     *reinterpret_cast<float4*>(lo + (c4 * MIDP + row) * 4) = l;
                 }
                 fence_async_smem();
-                mbar_arrive(&a_full[buf]);
+#pragma unroll
+                for (int k = 0; k < NPROD / 128; ++k) mbar_arrive(&a_full[buf]);    // barrier counts NPROD arrivals
             }
 #pragma unroll
             for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
@@ -342,6 +377,15 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_kernel(const Co
     }
     tc_fence_before();
     __syncthreads();
+#ifdef ADEC_TIMELINE
+    if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) {
+        const int ng = n_g1 + n_g2 < 64 ? n_g1 + n_g2 : 64;
+        printf("TIMELINE NT=%d fuse=%d groups=%d pieces=%d end=%u\n", NT, (int)FUSE, n_g1 + n_g2, a.n_pieces, (unsigned)(clock64() - tl0_));
+        for (int i = 0; i < ng; ++i)
+            printf(" g%02d tma %6u | mma ready %6u issued %6u | drain got %6u done %6u\n", i, tl_[0][i], tl_[1][i], tl_[2][i], tl_[4][i], tl_[5][i]);
+        for (int i = 0; i < a.n_pieces && i < 64; ++i) printf(" piece %d produced %6u\n", i, tl_[3][i]);
+    }
+#endif
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 

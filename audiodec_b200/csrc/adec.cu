@@ -92,12 +92,12 @@ const ConvKernelCfg* find_conv_kernel(int CW, int CO, bool fuse) {
 }
 
 // tensor-core (tcgen05, 3xTF32) instantiations: NT = output-channel tile (UMMA N)
-template <int NT, bool F>
+template <int NT, bool F, int PRE>
 cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
-    auto kern = tc_conv_kernel<NT, F>;
+    auto kern = tc_conv_kernel<NT, F, PRE>;
 #ifdef ADEC_TIMELINE
     constexpr int kMaxDyn = 227 * 1024 - 2048;   // room for the static timeline buffer
 #else
@@ -108,20 +108,24 @@ cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
+    if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
     kern<<<grid, TcCfg<NT>::THREADS, smem_bytes, s>>>(a);
     return cudaGetLastError();
 }
 
-struct TcKernelCfg { int NT, KS, stages; bool fuse; ConvLaunchFn fn; };
+struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; ConvLaunchFn fn; };
 #define ADEC_TC(NT) \
-    {NT, TC_CP, TcCfg<NT>::STAGES, false, launch_tc<NT, false>}, {NT, TC_CP, TcCfg<NT>::STAGES, true, launch_tc<NT, true>}
+    {NT, TC_CP, TcCfg<NT>::STAGES, true, ACT_ELU, launch_tc<NT, true, ACT_ELU>}, \
+    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_NONE, launch_tc<NT, false, ACT_NONE>}, \
+    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_ELU, launch_tc<NT, false, ACT_ELU>}, \
+    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_LRELU, launch_tc<NT, false, ACT_LRELU>}, \
+    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_NORM, launch_tc<NT, false, ACT_NORM>}
 const TcKernelCfg kTcKernels[] = {ADEC_TC(128), ADEC_TC(64), ADEC_TC(32)};
 constexpr int kTcMaxFuse = 128;    // residual units wider than this run as two launches on the tensor-core path
 
-const TcKernelCfg* find_tc_kernel(int NT, bool fuse) {
+const TcKernelCfg* find_tc_kernel(int NT, bool fuse, int pre) {
     for (const auto& k : kTcKernels)
-        if (k.NT == NT && k.fuse == fuse) return &k;
+        if (k.NT == NT && k.fuse == fuse && k.pre == pre) return &k;
     return nullptr;
 }
 
@@ -388,8 +392,8 @@ int pick_piece_width(const Op& op) {
 // choose the kernel instantiation, pack + upload weights, allocate state
 int finalize_op_tc(adec_handle* h, Op* op) {
     const int NT = op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
-    op->tc = find_tc_kernel(NT, op->fuse);
-    if (!op->tc || (op->fuse && NT != op->Cout)) return h->fail(op->name + ": no tensor-core kernel");
+    op->tc = find_tc_kernel(NT, op->fuse, op->pre_act);
+    if (!op->tc || (op->fuse && (NT != op->Cout || op->mid_act != op->pre_act))) return h->fail(op->name + ": no tensor-core kernel");
     const int KS = op->tc->KS, CP = TC_CP;
     op->n_pieces = op->Cin_eff / CP;
     op->n_co_tiles = op->Cout / NT;

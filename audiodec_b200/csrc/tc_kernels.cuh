@@ -82,7 +82,15 @@ struct TcCfg {
     static constexpr int NCOL = NT / NDG;                                   // accumulator registers per drain thread
 };
 
-template <int NT, bool FUSE>
+template <int ACT>
+__device__ __forceinline__ float4 apply_act_t(float4 v, float slope) {
+    if (ACT == ACT_ELU) { v.x = act_elu(v.x); v.y = act_elu(v.y); v.z = act_elu(v.z); v.w = act_elu(v.w); }
+    if (ACT == ACT_LRELU) { v.x = act_lrelu(v.x, slope); v.y = act_lrelu(v.y, slope); v.z = act_lrelu(v.z, slope); v.w = act_lrelu(v.w, slope); }
+    return v;
+}
+
+// PRE: pre-activation applied to chunk rows while the window is written (also the residual unit's mid activation)
+template <int NT, bool FUSE, int PRE>
 __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_conv_kernel(const ConvArgs a) {
     using Cfg = TcCfg<NT>;
     constexpr int S = Cfg::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG, NCOL = Cfg::NCOL;
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 1);
+            mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 2);   // both MMA warps release a piece
             mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG);
         }
         mbar_fence_init();
@@ -151,8 +159,11 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                 TL(0, c);
             }
         }
-    } else if (warp == 1) {
-        // ------------------------------------------------ MMA issuer: whole warp runs the loop (uniform), one lane issues
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------ MMA issuers: two warps take alternate groups (= alternate TMEM
+        // partials), so one is already past its barrier waits when the other's MMAs leave the queue.  Whole warp runs the
+        // loop (uniform datapath), one elected lane issues.
+        const int mw = warp - 1;
         int c = 0, gp = 0;
         const uint32_t b_lbo = (uint32_t)NT * 16u;
         const uint32_t abuf0_u = smem_u32(abuf0), abuf1_u = smem_u32(abuf1), bst_u = smem_u32(bst);
@@ -166,6 +177,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                 const uint32_t a_hi = buf ? abuf1_u : abuf0_u;
                 const uint32_t a_lo = a_hi + (uint32_t)(CP / 4) * lbo;     // lo block follows the hi block
                 for (int tap = 0; tap < taps; ++tap, ++c) {
+                    if ((c & 1) != mw) continue;
                     const int s = c % S, pb = c & 1;
                     mbar_wait(&b_full[s], (c / S) & 1, 300 + c);
                     if (c >= 2) mbar_wait(&p_empty[pb], ((c >> 1) - 1) & 1, 400 + c);
@@ -191,11 +203,12 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                                       umma_desc(b_hi + (uint32_t)(k8 * 2) * b_lbo, b_lbo), IDESC, 1u);
                         umma_commit(&b_empty[s]);       // weight stage free once these MMAs retire
                         umma_commit(&p_full[pb]);       // partial ready for the drain warps
-                        if (tap == taps - 1) umma_commit(&a_empty[buf]);   // activation piece free
                         TL(2, c);
                     }
                     __syncwarp();
                 }
+                if (elect_one()) umma_commit(&a_empty[buf]);   // this warp's MMAs on the piece (if any) have retired
+                __syncwarp();
             }
         }
     } else if (warp >= 4 && warp < DRAIN0) {
@@ -238,13 +251,13 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                         const long long i = (long long)(j0 + m) * a.RG + r;
                         float4 x4 = v[u];
                         if (i >= a.P && i - a.P < a.T) {        // chunk rows get the pre-activation; history rows already have it
-                            if (a.pre_act == ACT_NORM) {
+                            if (PRE == ACT_NORM) {
                                 const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
                                 const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
                                 x4.x = __fdiv_rn(x4.x - mu.x, sc.x); x4.y = __fdiv_rn(x4.y - mu.y, sc.y);
                                 x4.z = __fdiv_rn(x4.z - mu.z, sc.z); x4.w = __fdiv_rn(x4.w - mu.w, sc.w);
                             } else {
-                                x4 = apply_act(x4, a.pre_act, a.slope);
+                                x4 = apply_act_t<PRE>(x4, a.slope);
                             }
                         }
                         const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
@@ -271,13 +284,13 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                     v = *reinterpret_cast<const float4*>(sg + i * a.st_ld + ci);
                 } else {
                     v = __ldg(reinterpret_cast<const float4*>(xg + (i - a.P) * a.ldx + ci));
-                    if (a.pre_act == ACT_NORM) {
+                    if (PRE == ACT_NORM) {
                         const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
                         const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
                         v.x = __fdiv_rn(v.x - mu.x, sc.x); v.y = __fdiv_rn(v.y - mu.y, sc.y);
                         v.z = __fdiv_rn(v.z - mu.z, sc.z); v.w = __fdiv_rn(v.w - mu.w, sc.w);
                     } else {
-                        v = apply_act(v, a.pre_act, a.slope);
+                        v = apply_act_t<PRE>(v, a.slope);
                     }
                 }
                 *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + ci) = v;
@@ -331,8 +344,8 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                 float* lo = hi + CP * MIDP;
 #pragma unroll
                 for (int c4 = 0; c4 < 8; ++c4) {
-                    const float4 m4 = apply_act(make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1], racc[pl * CP + c4 * 4 + 2],
-                                                            racc[pl * CP + c4 * 4 + 3]), a.mid_act, a.slope);
+                    const float4 m4 = apply_act_t<PRE>(make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1], racc[pl * CP + c4 * 4 + 2],
+                                                                   racc[pl * CP + c4 * 4 + 3]), a.slope);
                     const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
                     const float4 l = make_float4(tf32_rna(m4.x - h.x), tf32_rna(m4.y - h.y), tf32_rna(m4.z - h.z), tf32_rna(m4.w - h.w));
                     *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
@@ -352,7 +365,10 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
             const int co_l = co_tile * NT + dg * NCOL;          // channel within the group
             if (a.bias) {
 #pragma unroll
-                for (int i = 0; i < NCOL; ++i) racc[i] += __ldg(a.bias + g * a.Cout_g + co_l + i);
+                for (int i = 0; i < NCOL / 4; ++i) {
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + g * a.Cout_g + co_l) + i);
+                    racc[4 * i] += b4.x; racc[4 * i + 1] += b4.y; racc[4 * i + 2] += b4.z; racc[4 * i + 3] += b4.w;
+                }
             }
             if (a.res) {
                 const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;

@@ -57,6 +57,8 @@ SYMBOLS = {
     "adec_hop_length": (c_int, [c_void_p]),
     "adec_codec_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "adec_launch_count": (c_int64, [c_void_p]),
+    "adec_profile": (c_int, [c_void_p, c_int]),
+    "adec_profile_report": (c_int, [c_void_p, c_char_p, c_int]),
     "adec_test_causal_conv": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                                       c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "adec_test_residual_unit": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),

@@ -117,6 +117,22 @@ class _StreamGeneratorBase:
     def launch_count(self):
         return int(self._lib.adec_launch_count(self._h)) if self._h is not None else 0
 
+    def profile(self, enable=True):
+        """start/stop per-launch CUDA-event timing (adec_profile)."""
+        self._ready()
+        _check(self._lib.adec_profile(self._h, int(enable)), self._h)
+
+    def profile_report(self):
+        """[(op name, ms, algorithmic bytes)] for every launch recorded since profile(True)."""
+        self._ready()
+        buf = ctypes.create_string_buffer(1 << 20)
+        _check(self._lib.adec_profile_report(self._h, buf, len(buf)), self._h)
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, ms, nbytes = line.split("\t")
+            rows.append((name, float(ms), float(nbytes)))
+        return rows
+
     def reset_buffer(self):
         """AudioDec.py:250-256 / HiFiGAN.py:298-305."""
         self._ready()

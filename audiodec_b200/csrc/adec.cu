@@ -109,8 +109,18 @@ cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t
         configured[dev] = true;
     }
     if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
-    kern<<<grid, TcCfg<NT>::THREADS, smem_bytes, s>>>(a);
-    return cudaGetLastError();
+    constexpr int CL = TcCfg<NT>::CLUSTER;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((grid.x + CL - 1) / CL * CL, grid.y, grid.z);     // padded tiles are fully masked in the kernel
+    cfg.blockDim = dim3(TcCfg<NT>::THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
 struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; ConvLaunchFn fn; };
@@ -202,6 +212,10 @@ struct adec_handle {
     float *d_mean = nullptr, *d_scale = nullptr;
     int* d_err = nullptr;
     int64_t launches = 0;
+    bool profiling = false;       // per-op CUDA-event timing (adec_profile)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+    std::vector<std::string> prof_names;
+    std::vector<double> prof_bytes;   // algorithmic bytes of each recorded launch (SURVEY 8(d) per-layer model)
     // host-path scratch
     DevBuf hx, hz, hzq, hy;
     long long* hidx = nullptr;
@@ -537,6 +551,11 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
         const float* st_in = op.st[op.cur];
         float* st_out = op.st[op.cur ^ 1];
         cudaError_t e = cudaSuccess;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (h->profiling) {
+            cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+            cudaEventRecord(ev0, rc.stream);
+        }
         if (op.kind == OP_STEM) {
             StemArgs a{};
             a.x = xin; a.x_bs = T; a.st_in = st_in; a.st_out = st_out; a.T = T;
@@ -582,6 +601,18 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
         }
         if (e != cudaSuccess) return h->fail(fmt("launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e)));
         ++h->launches;
+        if (h->profiling) {
+            cudaEventRecord(ev1, rc.stream);
+            h->prof_events.emplace_back(ev0, ev1);
+            h->prof_names.push_back(op.name);
+            // algorithmic bytes: 4*(Cin*Tin + Cout*Tout [+ Cout*Tout residual]) per stream (fused unit: its two convs + skip)
+            const double cin = op.kind == OP_STEM ? 1 : (double)op.G * op.Cin_eff / std::max(1, op.RG) * (op.shared_in ? 1.0 / op.G : 1.0);
+            const double cout = op.kind == OP_HEAD ? 1 : (double)op.G * op.Cout;
+            double bytes = 4.0 * rc.B * (cin * T + cout * Tout);
+            if (op.fuse) bytes += 4.0 * rc.B * (3.0 * cout * Tout);      // mid write+read (1x1 conv in/out) and the skip read
+            else if (op.res_buf >= 0) bytes += 4.0 * rc.B * cout * Tout;
+            h->prof_bytes.push_back(bytes);
+        }
         if (op.P > 0) op.cur ^= 1;
         T = Tout * op.up;
     }
@@ -1080,6 +1111,29 @@ int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int
 }
 
 int64_t adec_launch_count(const adec_handle* h) { return h ? h->launches : 0; }
+
+int adec_profile(adec_handle* h, int enable) {
+    if (!h) return 1;
+    for (auto& ev : h->prof_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+    h->prof_events.clear(); h->prof_names.clear(); h->prof_bytes.clear();
+    h->profiling = enable != 0;
+    return 0;
+}
+
+int adec_profile_report(adec_handle* h, char* buf, int buf_len) {
+    if (!h || !buf || buf_len < 2) return 1;
+    DeviceGuard dg(h->device);
+    std::string out;
+    for (size_t i = 0; i < h->prof_events.size(); ++i) {
+        if (cudaEventSynchronize(h->prof_events[i].second) != cudaSuccess) return h->fail("profile: event sync failed");
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, h->prof_events[i].first, h->prof_events[i].second);
+        out += fmt("%s\t%.6f\t%.0f\n", h->prof_names[i].c_str(), ms, h->prof_bytes[i]);
+    }
+    if ((int)out.size() + 1 > buf_len) return h->fail("profile: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return 0;
+}
 
 // -------------------------------------------------------------------------------------------------
 // single-layer entry points for the unit tests (HOST pointers, reference layouts)

@@ -42,6 +42,25 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// commit that arrives on the same barrier offset in every CTA of `mask` (weights are shared by the cluster)
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(mask)
+                 : "memory");
+}
+// bulk copy whose bytes (and mbarrier complete_tx) land at the same CTA-relative offsets in every CTA of `mask`
+__device__ __forceinline__ void bulk_g2s_mc(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -73,7 +92,8 @@ constexpr int TC_MIDP = 129;      // row pitch (rows) of the 1x1 conv's activate
 template <int NT>
 struct TcCfg {
     static constexpr int STAGES = NT == 64 ? 4 : 3;
-    static constexpr int MIN_CTAS = NT == 32 ? 2 : 1;                       // co-resident CTAs hide each other's serial phases
+    static constexpr int MIN_CTAS = NT == 32 ? 2 : 1;
+    static constexpr int CLUSTER = 1;                       // CTAs (adjacent time tiles) sharing one weight stream                       // co-resident CTAs hide each other's serial phases
     static constexpr int B_STAGE_FLOATS = 2 * TC_CP * NT;                   // hi | lo
     static constexpr int NDG = NT == 128 ? 2 : 1;                           // drain warpgroups (each owns NT/NDG columns)
     static constexpr int NPROD = NT == 128 ? 128 : 256;                     // activation-producer threads
@@ -122,8 +142,11 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
     const int n_g1 = a.n_pieces * a.Ktaps;                          // groups (= weight stages) of GEMM 1
     const int n_g2 = FUSE ? NT / CP : 0;                            // groups of the fused 1x1 conv
 
+    // Clusters along the time axis share the weight stream: every CTA fetches 1/CL of each stage and multicasts it.
+    const uint32_t CL = cluster_nctarank(), crank = cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << CL) - 1u);
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], CL); }   // freed when ALL CTAs consumed it
         for (int i = 0; i < 2; ++i) {
             mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 2);   // both MMA warps release a piece
             mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG);
@@ -136,6 +159,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // peers' barriers are initialised before anyone multicasts into them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 #ifdef ADEC_TIMELINE
@@ -155,7 +179,12 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                 if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1, 100 + c);
                 const float* src = c < n_g1 ? w1 + (long long)c * BST : a.w2 + (long long)(c - n_g1) * BST;
                 mbar_arrive_expect_tx(&b_full[s], BST * 4);
-                bulk_g2s(bst + s * BST, src, BST * 4, &b_full[s]);
+                if (CL == 1) {
+                    bulk_g2s(bst + s * BST, src, BST * 4, &b_full[s]);
+                } else {
+                    const uint32_t slice = (uint32_t)BST / CL;      // floats
+                    bulk_g2s_mc(bst + s * BST + crank * slice, src + crank * slice, slice * 4, &b_full[s], cmask);
+                }
                 TL(0, c);
             }
         }
@@ -201,7 +230,8 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                         for (int k8 = 0; k8 < CP / 8; ++k8)
                             umma_tf32(acc, umma_desc(a_hi + (uint32_t)(k8 * 2) * lbo + row_off, lbo),
                                       umma_desc(b_hi + (uint32_t)(k8 * 2) * b_lbo, b_lbo), IDESC, 1u);
-                        umma_commit(&b_empty[s]);       // weight stage free once these MMAs retire
+                        if (CL == 1) umma_commit(&b_empty[s]);       // weight stage free once these MMAs retire
+                        else umma_commit_mc(&b_empty[s], cmask);     // ... in every CTA of the cluster
                         umma_commit(&p_full[pb]);       // partial ready for the drain warps
                         TL(2, c);
                     }
@@ -272,7 +302,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
             if (pt == 0) TL(3, p);
         }
         // ---- new causal state (conv_layer.py:155), independent of the MMA pipeline
-        if (blockIdx.x == gridDim.x - 1 && co_tile == 0 && g < a.st_groups && a.P > 0) {
+        if ((int)blockIdx.x == (a.Tout - 1) / TT && co_tile == 0 && g < a.st_groups && a.P > 0) {   // grid.x may be padded to the cluster size
             float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
             const int nvec = a.P * (a.Cin / 4);
             for (int idx = pt; idx < nvec; idx += NPROD) {
@@ -393,6 +423,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();      // nobody exits while a peer can still multicast into / arrive on its smem
 #ifdef ADEC_TIMELINE
     if (tid == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0) {
         const int ng = n_g1 + n_g2 < 64 ? n_g1 + n_g2 : 64;

@@ -190,6 +190,29 @@ def run_ours(args):
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
     F = idx_h.shape[-1]
 
+    # ---- per-launch CUDA-event timing of one extra step (same inputs, same stream): which kernel dominates, and its
+    #      achieved algorithmic GB/s.  Outside the timed region so the events do not perturb `value`.
+    prof = None
+    if rank == 0:
+        tx.profile(True), dec.profile(True)
+        for i in range(2):
+            step(i)
+        torch.cuda.synchronize(dev)
+        rows = tx.profile_report() + dec.profile_report()
+        tx.profile(False), dec.profile(False)
+        agg = {}
+        for name, ms, nbytes in rows:
+            a = agg.setdefault(name, [0, 0.0, nbytes])
+            a[0] += 1
+            a[1] += ms
+        tot = sum(v[1] for v in agg.values())
+        top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        dname, (dn, dms, dbytes) = top[0]
+        prof = {"kernel": dname, "launch_ms": dms / dn, "alg_bytes_per_launch": dbytes, "share_of_step": dms / tot,
+                "conv_kernels_share_of_step": sum(v[1] for k, v in agg.items() if "res_units" in k or ".conv" in k or "project" in k
+                                                  or "blocks" in k or "upsamples" in k) / tot,
+                "top5": [{"op": k, "ms": v[1] / v[0], "GBps": v[2] / (v[1] / v[0]) / 1e6} for k, v in top[:5]]}
+
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -201,6 +224,16 @@ def run_ours(args):
     per_gpu = value / world
     alg_b = ALG_BYTES_PER_SAMPLE[args.workload]
     achieved = alg_b * per_gpu / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if prof and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        for key, val in tj.items():
+            if key != "_comment" and key in prof["kernel"]:
+                traffic = val
+    k_achieved = prof["alg_bytes_per_launch"] / (prof["launch_ms"] * 1e-3) / 1e9 if prof else achieved
+    conv_path = os.environ.get("ADEC_CONV_PATH", "tc")
     line = {
         "metric": "48 kHz audio samples/s, encode+quantize+lookup+decode (% HBM roofline in `roofline`)",
         "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -215,12 +248,20 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": B * T * 4,
                 "d2h_bytes_per_step": B * F * 300 * 4 + 8 * B * F * 8, "ms_per_step": ms_e2e / args.steps,
                 "api": "audiodec_b200.codec.codec_host -> adec_codec_host (pinned host buffers, per GPU)"},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "kernel": "conv_gemm_kernel family (every conv layer of the step; >95% of step time)",
-                     "model": f"algorithmic bytes {alg_b:.1f} B/sample (SURVEY.md 8(d) per-conv-layer model) x samples per step / step time, per GPU",
-                     "fp32_ffma_tflops": ALG_FLOP_PER_SAMPLE[args.workload] * per_gpu / 1e12,
+        "roofline": {"bound": "hbm", "achieved": k_achieved, "peak": peak, "unit": "GB/s", "frac": k_achieved / peak,
+                     "traffic": traffic, "peak_source": peak_src,
+                     "kernel": (("tc_conv_kernel (tcgen05 3xTF32)" if conv_path != "ffma" else "conv_gemm_kernel (fp32 FFMA)")
+                                + " launch of " + (prof["kernel"] if prof else "?")),
+                     "kernel_launch_ms": prof["launch_ms"] if prof else None,
+                     "kernel_alg_bytes_per_launch": prof["alg_bytes_per_launch"] if prof else None,
+                     "kernel_share_of_step": prof["share_of_step"] if prof else None,
+                     "conv_kernels_share_of_step": prof["conv_kernels_share_of_step"] if prof else None,
+                     "top5_launches": prof["top5"] if prof else None,
+                     "step": {"achieved": achieved, "frac": achieved / peak,
+                              "model": f"whole step: {alg_b:.1f} algorithmic B/sample (SURVEY.md 8(d) per-conv-layer model) x samples/s per GPU"},
+                     "useful_tflops": ALG_FLOP_PER_SAMPLE[args.workload] * per_gpu / 1e12,
                      "fp32_ffma_peak_tflops_nominal": FFMA_PEAK_TFLOPS},
+        "conv_path": conv_path,
         "clocks": clocks,
     }
     if args.cpu_baseline:

@@ -109,6 +109,12 @@ int adec_codec_host(adec_handle *enc, adec_handle *dec, const float *x_host, int
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t adec_launch_count(const adec_handle *h);
 
+/* Per-launch CUDA-event timing on the handle's stream (bench.py's roofline leg).  adec_profile(h,1) starts
+ * recording around every kernel launch, adec_profile(h,0) stops and clears.  adec_profile_report writes one line
+ * per recorded launch: "<op name>\t<ms>\t<algorithmic bytes>\n" (bytes per SURVEY.md 8(d)'s per-layer model). */
+int adec_profile(adec_handle *h, int enable);
+int adec_profile_report(adec_handle *h, char *buf, int buf_len);
+
 /* -- unit-test entry points for single layers (tests/test_layers_gpu.py) ------- */
 /* One causal conv (layers/conv_layer.py:153-156) on device buffers, channels-first in/out like the
  * reference: x (B,Cin,T) HOST pointers, w (Cout,Cin/groups,K), state (B,Cin,(K-1)*dil) updated in place,

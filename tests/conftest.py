@@ -28,3 +28,11 @@ def symad_sd():
 def hifigan_sd():
     from audiodec_b200 import synthetic as S
     return S.hifigan_state_dict(seed=1)
+
+
+@pytest.fixture(params=["tc", "ffma"])
+def conv_path(request, monkeypatch):
+    """Both conv engines behind the same C ABI: tcgen05 3xTF32 (default) and the CUDA-core FFMA kernels.  The library
+    reads ADEC_CONV_PATH when a handle is created."""
+    monkeypatch.setenv("ADEC_CONV_PATH", request.param)
+    return request.param

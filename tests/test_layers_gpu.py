@@ -26,7 +26,7 @@ def lib():
 
 
 @pytest.mark.parametrize("name", ["conv_k7_d3", "conv_k6_s3", "conv_k10_s5_ragged", "conv_k11_d5_g3", "conv_short_chunk"])
-def test_causal_conv_matches_reference(lib, golden_dir, name):
+def test_causal_conv_matches_reference(lib, golden_dir, name, conv_path):
     from audiodec_b200 import _lib
     c = _case(np.load(os.path.join(golden_dir, "layers.npz")), name)
     cin, cout, k, s, d, grp, T = [int(v) for v in c["cfg"]]
@@ -44,7 +44,7 @@ def test_causal_conv_matches_reference(lib, golden_dir, name):
 
 
 @pytest.mark.parametrize("name", ["convtr_s5", "convtr_s3"])
-def test_causal_convtr_matches_reference(lib, golden_dir, name):
+def test_causal_convtr_matches_reference(lib, golden_dir, name, conv_path):
     from audiodec_b200 import _lib
     c = _case(np.load(os.path.join(golden_dir, "layers.npz")), name)
     cin, cout, k, s, _, _, T = [int(v) for v in c["cfg"]]
@@ -79,7 +79,7 @@ def test_conv_with_preactivation_and_batch(lib):
 
 
 @pytest.mark.parametrize("C,d,T,B", [(32, 1, 700, 2), (64, 3, 300, 1), (64, 9, 130, 2), (128, 9, 260, 1)])
-def test_residual_unit_fused(lib, C, d, T, B):
+def test_residual_unit_fused(lib, C, d, T, B, conv_path):
     """Fused residual unit (residual_unit.py:78-81) against torch fp32 on CPU, two consecutive chunks."""
     from audiodec_b200 import _lib
     torch.manual_seed(C + d)

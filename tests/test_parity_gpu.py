@@ -48,7 +48,7 @@ def _run(tx, rx, dec, x):
     return z.cpu(), idx.cpu(), zq.cpu(), y.cpu()
 
 
-def test_symad_oneshot_golden(golden_dir, symad_sd):
+def test_symad_oneshot_golden(golden_dir, symad_sd, conv_path):
     g = np.load(os.path.join(golden_dir, "symad_oneshot.npz"))
     tx, rx, dec, zq0 = _codec(symad_sd)
     assert tuple(zq0.shape) == (1, 28, 64)
@@ -61,7 +61,7 @@ def test_symad_oneshot_golden(golden_dir, symad_sd):
     np.testing.assert_allclose(y.numpy(), g["y"], atol=WAVE_TOL)
 
 
-def test_symad_stream_chunks_golden(golden_dir, symad_sd):
+def test_symad_stream_chunks_golden(golden_dir, symad_sd, conv_path):
     g = np.load(os.path.join(golden_dir, "symad_stream.npz"))
     tx, rx, dec, _ = _codec(symad_sd)
     x = torch.from_numpy(g["x"])
@@ -90,7 +90,7 @@ def test_symad_batch3_golden(golden_dir, symad_sd):
     np.testing.assert_allclose(y.numpy(), g["y"], atol=WAVE_TOL)
 
 
-def test_v1_vocoder_golden(golden_dir, symad_sd, hifigan_sd):
+def test_v1_vocoder_golden(golden_dir, symad_sd, hifigan_sd, conv_path):
     g = np.load(os.path.join(golden_dir, "v1_oneshot.npz"))
     tx, rx, dec, _ = _codec(symad_sd, hifigan_sd)
     z, idx, zq, y = _run(tx, rx, dec, torch.from_numpy(g["x"]))

@@ -265,7 +265,7 @@ def run_ours(args):
         "clocks": clocks,
     }
     if args.cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(args.workload, n_utt=args.cpu_utts)
+        line["cpu_baseline"] = cpu_baseline(args.workload, n_utt=args.cpu_utts, threads=best_cpu_threads(args.workload))
     print(json.dumps(line), flush=True)
 
 
@@ -298,13 +298,28 @@ def cpu_baseline(workload, n_utt=4, seconds=1.0, threads=None):
             "realtime_factor": n_utt * T / dt / SAMPLE_RATE}
 
 
+def best_cpu_threads(workload):
+    """The reference's demo default is 4 threads (demoFile.py:28); more threads help up to a point and then hurt (small
+    convs, oversubscription).  Pick the fastest of a few counts on a 0.25 s clip so the CPU arm is not handicapped."""
+    import torch
+    ncpu = os.cpu_count() or 1
+    cands = sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu})
+    best, best_v = cands[0], 0.0
+    for c in cands:
+        v = cpu_baseline(workload, n_utt=1, seconds=0.25, threads=c)["value"]
+        if v > best_v:
+            best, best_v = c, v
+    torch.set_num_threads(best)
+    return best
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
     import torch
     world = int(os.environ.get("WORLD_SIZE", 1))
-    torch.set_num_threads(os.cpu_count() or 1)
+    best_cpu_threads(args.workload)
     per = []
     n_utt = 2
     for _ in range(args.warmup):

@@ -43,21 +43,25 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* b) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* b, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires)
+// instead of spinning - polling loops were 30-40 % of all issued instructions in the first tensor-core profile.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
     uint32_t ok;
     asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
         : "=r"(ok)
-        : "r"(smem_u32(b)), "r"(parity)
+        : "r"(smem_u32(b)), "r"(parity), "r"(0x989680u)
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.
+// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.  The clock is only consulted every
+// 64 failed probes so the common path stays a 2-instruction loop.
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(b, parity)) return;
     const long long t0 = clock64();
-    while (!mbar_try_wait(b, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+    for (unsigned it = 1;; ++it) {
+        if (mbar_try_wait(b, parity)) return;
+        if ((it & 63u) == 0 && clock64() - t0 > 4000000000LL) {
             printf("adec: mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x);
             __trap();
@@ -74,14 +78,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// nn.ELU(alpha=1): x > 0 ? x : expm1(x).  expm1f() costs ~40 instructions; this is ~12 and stays within ~1e-7 ABSOLUTE
-// of it (degree-5 Taylor near zero where exp(x)-1 would cancel, ex2.approx elsewhere) - the same order as the fp32
-// rounding of the O(1) activations it sits next to.
+// nn.ELU(alpha=1): x > 0 ? x : expm1(x).  expm1f() costs ~40 instructions and the elementwise work, not the tensor
+// pipe, bounds the narrow layers; ex2.approx(x*log2e) - 1 is 4 instructions and within 2.4e-7 ABSOLUTE of expm1 on
+// (-inf, 0] (2^-22 relative error of ex2.approx on a value <= 1) - the same order as the fp32 rounding of the O(1)
+// activations it is summed with.  Parity margins: tests/test_layers_gpu.py (1e-5 on a fused unit), golden indices.
 __device__ __forceinline__ float act_elu(float v) {
     const float e = __expf(v) - 1.0f;
-    const float p = v * fmaf(v, fmaf(v, fmaf(v, fmaf(v, 1.0f / 120.0f, 1.0f / 24.0f), 1.0f / 6.0f), 0.5f), 1.0f);
-    const float neg = v > -0.25f ? p : e;
-    return v > 0.f ? v : neg;
+    return v > 0.f ? v : e;
 }
 __device__ __forceinline__ float act_lrelu(float v, float s) { return v > 0.f ? v : v * s; }
 

@@ -262,38 +262,63 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
             const float* xrow = xg + ci;
             float* hcol = hi + (c4 * wrp) * 4;
             float* lcol = lo + (c4 * wrp) * 4;
-            for (int mb = m0; mb < wrows; mb += RPP * UNR) {
-                float4 v[UNR];
+            // interior tiles (no history rows, no rows past the chunk end) take the unchecked path
+            const long long i_first = (long long)j0 * a.RG + r;
+            const long long i_last = (long long)(j0 + wrows - 1) * a.RG + r;
+            if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM) {
+                const float* xp = xrow + (i_first - a.P + (long long)m0 * a.RG) * a.ldx;
+                const long long xstep = (long long)RPP * a.RG * a.ldx;
+                for (int mb = m0; mb < wrows; mb += RPP * UNR, xp += xstep * UNR) {
+                    float4 v[UNR];
 #pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int m = mb + u * RPP;
-                    const long long i = (long long)(j0 + m) * a.RG + r;
-                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (m < wrows) {
-                        if (i < a.P) v[u] = *reinterpret_cast<const float4*>(srow + i * a.st_ld);
-                        else if (i - a.P < a.T) v[u] = __ldg(reinterpret_cast<const float4*>(xrow + (i - a.P) * a.ldx));
+                    for (int u = 0; u < UNR; ++u)
+                        if (mb + u * RPP < wrows) v[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
+#pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int m = mb + u * RPP;
+                        if (m < wrows) {
+                            const float4 x4 = apply_act_t<PRE>(v[u], a.slope);
+                            const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
+                            const float4 l = make_float4(x4.x - h.x, x4.y - h.y, x4.z - h.z, x4.w - h.w);
+                            *reinterpret_cast<float4*>(hcol + m * 4) = h;
+                            *reinterpret_cast<float4*>(lcol + m * 4) = l;
+                        }
                     }
                 }
-#pragma unroll
-                for (int u = 0; u < UNR; ++u) {
-                    const int m = mb + u * RPP;
-                    if (m < wrows) {
+            } else {
+                for (int mb = m0; mb < wrows; mb += RPP * UNR) {
+                    float4 v[UNR];
+    #pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int m = mb + u * RPP;
                         const long long i = (long long)(j0 + m) * a.RG + r;
-                        float4 x4 = v[u];
-                        if (i >= a.P && i - a.P < a.T) {        // chunk rows get the pre-activation; history rows already have it
-                            if (PRE == ACT_NORM) {
-                                const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
-                                const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
-                                x4.x = __fdiv_rn(x4.x - mu.x, sc.x); x4.y = __fdiv_rn(x4.y - mu.y, sc.y);
-                                x4.z = __fdiv_rn(x4.z - mu.z, sc.z); x4.w = __fdiv_rn(x4.w - mu.w, sc.w);
-                            } else {
-                                x4 = apply_act_t<PRE>(x4, a.slope);
-                            }
+                        v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (m < wrows) {
+                            if (i < a.P) v[u] = *reinterpret_cast<const float4*>(srow + i * a.st_ld);
+                            else if (i - a.P < a.T) v[u] = __ldg(reinterpret_cast<const float4*>(xrow + (i - a.P) * a.ldx));
                         }
-                        const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
-                        const float4 l = make_float4(tf32_rna(x4.x - h.x), tf32_rna(x4.y - h.y), tf32_rna(x4.z - h.z), tf32_rna(x4.w - h.w));
-                        *reinterpret_cast<float4*>(hcol + m * 4) = h;
-                        *reinterpret_cast<float4*>(lcol + m * 4) = l;
+                    }
+    #pragma unroll
+                    for (int u = 0; u < UNR; ++u) {
+                        const int m = mb + u * RPP;
+                        if (m < wrows) {
+                            const long long i = (long long)(j0 + m) * a.RG + r;
+                            float4 x4 = v[u];
+                            if (i >= a.P && i - a.P < a.T) {        // chunk rows get the pre-activation; history rows already have it
+                                if (PRE == ACT_NORM) {
+                                    const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
+                                    const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
+                                    x4.x = __fdiv_rn(x4.x - mu.x, sc.x); x4.y = __fdiv_rn(x4.y - mu.y, sc.y);
+                                    x4.z = __fdiv_rn(x4.z - mu.z, sc.z); x4.w = __fdiv_rn(x4.w - mu.w, sc.w);
+                                } else {
+                                    x4 = apply_act_t<PRE>(x4, a.slope);
+                                }
+                            }
+                            const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
+                            const float4 l = make_float4(x4.x - h.x, x4.y - h.y, x4.z - h.z, x4.w - h.w);   // exact; the MMA reads its top 19 bits
+                            *reinterpret_cast<float4*>(hcol + m * 4) = h;
+                            *reinterpret_cast<float4*>(lcol + m * 4) = l;
+                        }
                     }
                 }
             }
@@ -377,7 +402,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                     const float4 m4 = apply_act_t<PRE>(make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1], racc[pl * CP + c4 * 4 + 2],
                                                                    racc[pl * CP + c4 * 4 + 3]), a.slope);
                     const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
-                    const float4 l = make_float4(tf32_rna(m4.x - h.x), tf32_rna(m4.y - h.y), tf32_rna(m4.z - h.z), tf32_rna(m4.w - h.w));
+                    const float4 l = make_float4(m4.x - h.x, m4.y - h.y, m4.z - h.z, m4.w - h.w);
                     *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
                     *reinterpret_cast<float4*>(lo + (c4 * MIDP + row) * 4) = l;
                 }

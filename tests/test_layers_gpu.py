@@ -75,7 +75,7 @@ def test_conv_with_preactivation_and_batch(lib):
         rc = lib.adec_test_causal_conv(0, _p(xn), B, cin, T, _p(wn), None, cout, k, 1, d, 1, act, slope, _p(stn), _p(y))
         assert rc == 0, _lib.last_error(None)
         np.testing.assert_allclose(y, ref.numpy(), atol=2e-5, rtol=0)
-        np.testing.assert_allclose(stn, torch.cat([st, f(x)], -1)[:, :, -(k - 1) * d:].numpy(), atol=1e-6)
+        np.testing.assert_allclose(stn, torch.cat([st, f(x)], -1)[:, :, -(k - 1) * d:].numpy(), atol=2e-6)
 
 
 @pytest.mark.parametrize("C,d,T,B", [(32, 1, 700, 2), (64, 3, 300, 1), (64, 9, 130, 2), (128, 9, 260, 1)])
@@ -96,7 +96,7 @@ def test_residual_unit_fused(lib, C, d, T, B, conv_path):
         y = np.zeros((B, C, T), np.float32)
         rc = lib.adec_test_residual_unit(0, _p(x.numpy().copy()), B, C, T, _p(w1.numpy().copy()), _p(w2.numpy().copy()), 7, d, _p(stn), _p(y))
         assert rc == 0, _lib.last_error(None)
-        np.testing.assert_allclose(y, ref.numpy(), atol=5e-6, rtol=0)
+        np.testing.assert_allclose(y, ref.numpy(), atol=1e-5, rtol=0)
         np.testing.assert_allclose(stn, st.numpy(), atol=1e-6)
 
 

@@ -20,6 +20,7 @@
 #include "../../include/audiodec_b200.h"
 #include "kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_persist.cuh"
 
 using namespace adec;
 
@@ -123,13 +124,29 @@ cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
-struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; ConvLaunchFn fn; };
+// persistent variant: one CTA per SM loops over (time tile, channel tile, stream) tiles
+typedef cudaError_t (*TcPersistFn)(const ConvArgs&, int, int, int, int, int, cudaStream_t);
+template <int NT, bool F, int PRE>
+cudaError_t launch_tcp(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tiles, int n_ctas, int smem_bytes, cudaStream_t s) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kern = tc_conv_persist_kernel<NT, F, PRE>;
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
+    kern<<<n_ctas, TcCfg<NT>::THREADS, smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
+    return cudaGetLastError();
+}
+
+struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; ConvLaunchFn fn; TcPersistFn pfn; };
+#define ADEC_TC1(NT, F, PRE) {NT, TC_CP, TcCfg<NT>::STAGES, F, PRE, launch_tc<NT, F, PRE>, launch_tcp<NT, F, PRE>}
 #define ADEC_TC(NT) \
-    {NT, TC_CP, TcCfg<NT>::STAGES, true, ACT_ELU, launch_tc<NT, true, ACT_ELU>}, \
-    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_NONE, launch_tc<NT, false, ACT_NONE>}, \
-    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_ELU, launch_tc<NT, false, ACT_ELU>}, \
-    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_LRELU, launch_tc<NT, false, ACT_LRELU>}, \
-    {NT, TC_CP, TcCfg<NT>::STAGES, false, ACT_NORM, launch_tc<NT, false, ACT_NORM>}
+    ADEC_TC1(NT, true, ACT_ELU), ADEC_TC1(NT, false, ACT_NONE), ADEC_TC1(NT, false, ACT_ELU), ADEC_TC1(NT, false, ACT_LRELU), \
+    ADEC_TC1(NT, false, ACT_NORM)
 const TcKernelCfg kTcKernels[] = {ADEC_TC(128), ADEC_TC(64), ADEC_TC(32)};
 constexpr int kTcMaxFuse = 128;    // residual units wider than this run as two launches on the tensor-core path
 
@@ -205,6 +222,8 @@ struct adec_handle {
     std::vector<Op> enc_ops, dec_ops;
     int n_streams = 1;
     bool use_tc = true;           // ADEC_CONV_PATH=ffma selects the CUDA-core kernels
+    int persist_mask = 32 | 64 | 128;  // ADEC_TC_PERSIST: bit mask of channel-tile widths (32|64|128) that use the persistent kernel
+    int n_sms = 148;
     DevBuf ws[3];
     std::vector<void*> owned;     // device allocations freed in destroy
     // rvq
@@ -592,7 +611,15 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
                 const size_t smem = 256 + sizeof(float) * ((size_t)op.tc->stages * 2 * op.tc->KS * op.tc->NT +
                                                            (size_t)2 * TC_CP * (wrp + buf1_rows));
                 dim3 grid((Tout + TC_TT - 1) / TC_TT, op.G * op.n_co_tiles, rc.B);
-                e = op.tc->fn(a, grid, (int)smem, rc.stream);
+                if (h->persist_mask & op.tc->NT) {
+                    const size_t psmem = 256 + sizeof(float) * ((size_t)op.tc->stages * 2 * op.tc->KS * op.tc->NT + (size_t)4 * TC_CP * wrp +
+                                                                (op.fuse ? (size_t)2 * TC_CP * TC_MIDP : 0));
+                    const long long n_tiles = (long long)grid.x * grid.y * grid.z;
+                    const int n_ctas = (int)std::min<long long>(n_tiles, h->n_sms);
+                    e = op.tc->pfn(a, (int)grid.x, (int)grid.y, (int)n_tiles, n_ctas, (int)psmem, rc.stream);
+                } else {
+                    e = op.tc->fn(a, grid, (int)smem, rc.stream);
+                }
             } else {
                 const int TT = op.kc->TT;
                 dim3 grid((Tout + TT - 1) / TT, op.G * op.n_co_tiles, rc.B);
@@ -929,6 +956,8 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     h->cfg = *cfg;
     h->device = device;
     if (const char* pth = getenv("ADEC_CONV_PATH")) h->use_tc = strcmp(pth, "ffma") != 0;
+    if (const char* pm = getenv("ADEC_TC_PERSIST")) h->persist_mask = atoi(pm);
+    cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     DeviceGuard dg(device);
     if (cudaMalloc((void**)&h->d_err, sizeof(int)) != cudaSuccess || cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) {
         g_create_error = "cudaMalloc failed";

@@ -1,0 +1,359 @@
+// tc_conv_persist_kernel: persistent, cross-tile pipelined version of tc_conv_kernel (tc_kernels.cuh).
+//
+// Same math, same operand layouts, same grouped 3xTF32 accumulation.  What changes is the schedule: one CTA per SM
+// loops over output tiles, and every role keeps running counters so its mbarrier rings simply continue from one tile
+// into the next:
+//     producers   : run ahead on the next tile's activation window while the current tile is in its 1x1 conv / epilogue
+//     TMA         : keeps the weight ring full across tile boundaries
+//     MMA (2 warps): GEMM 1 of tile i+1 starts as soon as its window piece and a TMEM partial are free
+//     drain       : four TMEM partials (instead of two) let the MMAs run ahead while these warps convert the fused
+//                   intermediate or write the epilogue
+// The fused intermediate has its own smem buffer and barrier pair (m_full/m_empty) so that each barrier is waited on
+// by threads that observe every one of its phases (an mbarrier parity wait is only unambiguous for such a waiter).
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace adec {
+
+constexpr int TCP_NPB = 4;    // TMEM partial buffers
+
+template <int NT, bool FUSE, int PRE>
+__global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
+    using Cfg = TcCfg<NT>;
+    constexpr int S = Cfg::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG;
+    constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0, MIDP = TC_MIDP, NPB = TCP_NPB;
+    constexpr int NCOL = NT / NDG;                       // accumulator registers per drain thread
+    constexpr int PPG = NCOL / CP;                       // 32-column pieces owned by one drain group
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    constexpr uint32_t TMEM_COLS = NPB * NT;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);     // [S]   weights landed
+    uint64_t* b_empty = b_full + S;                                // [S]   weights consumed
+    uint64_t* w_full = b_empty + S;                                // [2]   window piece written
+    uint64_t* w_empty = w_full + 2;                                // [2]   window piece consumed
+    uint64_t* m_full = w_empty + 2;                                // [1]   fused-intermediate piece written
+    uint64_t* m_empty = m_full + 1;                                // [1]   ... consumed
+    uint64_t* p_full = m_empty + 1;                                // [NPB] TMEM partial complete
+    uint64_t* p_empty = p_full + NPB;                              // [NPB] TMEM partial drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + NPB);
+    float* bst = reinterpret_cast<float*>(smem_raw + 256);
+    const int wrows = TT + (a.Ktaps - 1) * a.dil;
+    const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
+    float* wbuf0 = bst + S * BST;
+    float* wbuf1 = wbuf0 + 2 * CP * wrp;
+    float* mbuf = wbuf1 + 2 * CP * wrp;                            // FUSE only: 2*CP*MIDP floats
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int n_g1 = a.n_pieces * a.Ktaps;
+    const int n_g2 = FUSE ? NT / CP : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], 2); }
+        mbar_init(m_full, 128); mbar_init(m_empty, 2);
+        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ weight producer
+        if (lane == 0) {
+            int c = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int y = (tile / n_xtiles) % n_ytiles;
+                const float* w1 = a.w + (long long)y * a.w_tile_floats;
+                for (int k = 0; k < n_g1 + n_g2; ++k, ++c) {
+                    const int s = c % S, it = c / S;
+                    if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1, 100);
+                    const float* src = k < n_g1 ? w1 + (long long)k * BST : a.w2 + (long long)(k - n_g1) * BST;
+                    mbar_arrive_expect_tx(&b_full[s], BST * 4);
+                    bulk_g2s(bst + s * BST, src, BST * 4, &b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1 || warp == 2) {
+        // ------------------------------------------------ MMA issuers (alternate groups)
+        const int mw = warp - 1;
+        int c = 0, wp = 0, mp = 0;
+        const uint32_t b_lbo = (uint32_t)NT * 16u;
+        const uint32_t wbuf0_u = smem_u32(wbuf0), wbuf1_u = smem_u32(wbuf1), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
+        auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off) {
+            const int s = c % S, pb = c % NPB;
+            mbar_wait(&b_full[s], (c / S) & 1, 300);
+            if (c >= NPB) mbar_wait(&p_empty[pb], ((c / NPB) - 1) & 1, 400);
+            tc_fence_after();
+            const uint32_t b_hi = bst_u + (uint32_t)s * (BST * 4u);
+            const uint32_t b_lo = b_hi + (uint32_t)CP * NT * 4u;
+            const uint32_t acc = tmem + (uint32_t)pb * NT;
+            if (elect_one()) {
+#pragma unroll
+                for (int k8 = 0; k8 < CP / 8; ++k8)
+                    umma_tf32(acc, umma_desc(a_lo + (uint32_t)(k8 * 2) * lbo + row_off, lbo), umma_desc(b_hi + (uint32_t)(k8 * 2) * b_lbo, b_lbo),
+                              IDESC, k8 ? 1u : 0u);
+#pragma unroll
+                for (int k8 = 0; k8 < CP / 8; ++k8)
+                    umma_tf32(acc, umma_desc(a_hi + (uint32_t)(k8 * 2) * lbo + row_off, lbo), umma_desc(b_lo + (uint32_t)(k8 * 2) * b_lbo, b_lbo),
+                              IDESC, 1u);
+#pragma unroll
+                for (int k8 = 0; k8 < CP / 8; ++k8)
+                    umma_tf32(acc, umma_desc(a_hi + (uint32_t)(k8 * 2) * lbo + row_off, lbo), umma_desc(b_hi + (uint32_t)(k8 * 2) * b_lbo, b_lbo),
+                              IDESC, 1u);
+                umma_commit(&b_empty[s]);
+                umma_commit(&p_full[pb]);
+            }
+            __syncwarp();
+        };
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const uint32_t lbo1 = (uint32_t)wrp * 16u;
+            for (int p = 0; p < a.n_pieces; ++p, ++wp) {
+                const int buf = wp & 1;
+                mbar_wait(&w_full[buf], (wp >> 1) & 1, 200);
+                const uint32_t a_hi = buf ? wbuf1_u : wbuf0_u;
+                const uint32_t a_lo = a_hi + (uint32_t)(CP / 4) * lbo1;
+                for (int tap = 0; tap < a.Ktaps; ++tap, ++c)
+                    if ((c & 1) == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)(tap * a.dil) * 16u);
+                if (elect_one()) umma_commit(&w_empty[buf]);
+                __syncwarp();
+            }
+            if (FUSE) {
+                const uint32_t lbo2 = (uint32_t)MIDP * 16u;
+                for (int p = 0; p < NT / CP; ++p, ++mp, ++c) {
+                    mbar_wait(m_full, mp & 1, 250);
+                    if ((c & 1) == mw) issue_group(mbuf_u, mbuf_u + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
+                    if (elect_one()) umma_commit(m_empty);
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp >= 4 && warp < DRAIN0) {
+        // ------------------------------------------------ activation producers
+        const int pt = tid - 128;
+        int wp = 0;
+        constexpr int RPP = NPROD / 8;
+        constexpr int UNR = 6;
+        const int c4 = pt & 7, m0 = pt >> 3;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
+            const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+            const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
+            const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
+            for (int p = 0; p < a.n_pieces; ++p, ++wp) {
+                const int buf = wp & 1;
+                if (wp >= 2) mbar_wait(&w_empty[buf], ((wp >> 1) - 1) & 1, 500);
+                float* hi = buf ? wbuf1 : wbuf0;
+                float* lo = hi + CP * wrp;
+                const int q = p * CP + c4 * 4;
+                int r = 0, ci = q;
+                if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
+                const float* srow = sg + ci;
+                const float* xrow = xg + ci;
+                float* hcol = hi + (c4 * wrp) * 4;
+                float* lcol = lo + (c4 * wrp) * 4;
+                const long long i_first = (long long)j0 * a.RG + r;
+                const long long i_last = (long long)(j0 + wrows - 1) * a.RG + r;
+                if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM) {
+                    const float* xp = xrow + (i_first - a.P + (long long)m0 * a.RG) * a.ldx;
+                    const long long xstep = (long long)RPP * a.RG * a.ldx;
+                    for (int mb = m0; mb < wrows; mb += RPP * UNR, xp += xstep * UNR) {
+                        float4 v[UNR];
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u)
+                            if (mb + u * RPP < wrows) v[u] = __ldg(reinterpret_cast<const float4*>(xp + u * xstep));
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) {
+                            const int m = mb + u * RPP;
+                            if (m < wrows) {
+                                const float4 x4 = apply_act_t<PRE>(v[u], a.slope);
+                                const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
+                                const float4 l = make_float4(x4.x - h.x, x4.y - h.y, x4.z - h.z, x4.w - h.w);
+                                *reinterpret_cast<float4*>(hcol + m * 4) = h;
+                                *reinterpret_cast<float4*>(lcol + m * 4) = l;
+                            }
+                        }
+                    }
+                } else {
+                    for (int mb = m0; mb < wrows; mb += RPP * UNR) {
+                        float4 v[UNR];
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) {
+                            const int m = mb + u * RPP;
+                            const long long i = (long long)(j0 + m) * a.RG + r;
+                            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (m < wrows) {
+                                if (i < a.P) v[u] = *reinterpret_cast<const float4*>(srow + i * a.st_ld);
+                                else if (i - a.P < a.T) v[u] = __ldg(reinterpret_cast<const float4*>(xrow + (i - a.P) * a.ldx));
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UNR; ++u) {
+                            const int m = mb + u * RPP;
+                            if (m < wrows) {
+                                const long long i = (long long)(j0 + m) * a.RG + r;
+                                float4 x4 = v[u];
+                                if (i >= a.P && i - a.P < a.T) {
+                                    if (PRE == ACT_NORM) {
+                                        const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
+                                        const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
+                                        x4.x = __fdiv_rn(x4.x - mu.x, sc.x); x4.y = __fdiv_rn(x4.y - mu.y, sc.y);
+                                        x4.z = __fdiv_rn(x4.z - mu.z, sc.z); x4.w = __fdiv_rn(x4.w - mu.w, sc.w);
+                                    } else {
+                                        x4 = apply_act_t<PRE>(x4, a.slope);
+                                    }
+                                }
+                                const float4 h = make_float4(tf32_rna(x4.x), tf32_rna(x4.y), tf32_rna(x4.z), tf32_rna(x4.w));
+                                const float4 l = make_float4(x4.x - h.x, x4.y - h.y, x4.z - h.z, x4.w - h.w);
+                                *reinterpret_cast<float4*>(hcol + m * 4) = h;
+                                *reinterpret_cast<float4*>(lcol + m * 4) = l;
+                            }
+                        }
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(&w_full[buf]);
+            }
+            // ---- new causal state (conv_layer.py:155)
+            if (xt == (a.Tout - 1) / TT && co_tile == 0 && g < a.st_groups && a.P > 0) {
+                float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
+                const int nvec = a.P * (a.Cin / 4);
+                for (int idx = pt; idx < nvec; idx += NPROD) {
+                    const int r = idx / (a.Cin / 4);
+                    const int ci = (idx - r * (a.Cin / 4)) * 4;
+                    const long long i = (long long)a.T + r;
+                    float4 v;
+                    if (i < a.P) {
+                        v = *reinterpret_cast<const float4*>(sg + i * a.st_ld + ci);
+                    } else {
+                        v = __ldg(reinterpret_cast<const float4*>(xg + (i - a.P) * a.ldx + ci));
+                        if (PRE == ACT_NORM) {
+                            const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
+                            const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);
+                            v.x = __fdiv_rn(v.x - mu.x, sc.x); v.y = __fdiv_rn(v.y - mu.y, sc.y);
+                            v.z = __fdiv_rn(v.z - mu.z, sc.z); v.w = __fdiv_rn(v.w - mu.w, sc.w);
+                        } else {
+                            v = apply_act_t<PRE>(v, a.slope);
+                        }
+                    }
+                    *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + ci) = v;
+                }
+            }
+        }
+    } else if (warp >= DRAIN0) {
+        // ------------------------------------------------ drain warps: register accumulation, fused intermediate, epilogue
+        const int dg = (warp - DRAIN0) >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        // Column ownership: piece pl of group dg is 32-column piece (pl*NDG + dg), so that consecutive intermediate
+        // pieces alternate between the groups and every group meets every m_empty phase in order.
+        float racc[NCOL];
+        int c = 0, m_seen = 0, mq = 0;
+        auto drain = [&](int ngroups) {
+            for (int gi = 0; gi < ngroups; ++gi, ++c) {
+                const int pb = c % NPB;
+                mbar_wait(&p_full[pb], (c / NPB) & 1, 600);
+                tc_fence_after();
+#pragma unroll
+                for (int pl = 0; pl < PPG; ++pl) {
+                    const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)(pl * NDG + dg) * CP;
+                    uint32_t r0[16], r1[16];
+                    tmem_ld16(taddr, r0);
+                    tmem_ld16(taddr + 16, r1);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        racc[pl * CP + i] = __fadd_rn(racc[pl * CP + i], __uint_as_float(r0[i]));
+                        racc[pl * CP + 16 + i] = __fadd_rn(racc[pl * CP + 16 + i], __uint_as_float(r1[i]));
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&p_empty[pb]);
+            }
+        };
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
+            const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+            drain(n_g1);
+            if (FUSE) {
+                // intermediate pieces in consumption order 0,1,2,...: piece q is written by group q % NDG.  The single
+                // buffer is free again once piece q-1 was consumed = completion #(mq+q-1) of m_empty; every thread walks
+                // through all completions in order.
+#pragma unroll
+                for (int q = 0; q < NT / CP; ++q) {
+                    const int need = mq + q;                 // completions that must have happened before piece q is written
+                    while (m_seen < need) { mbar_wait(m_empty, m_seen & 1, 700); ++m_seen; }
+                    if (q % NDG == dg) {
+                        const int pl = q / NDG;
+                        float* hi = mbuf;
+                        float* lo = hi + CP * MIDP;
+#pragma unroll
+                        for (int c4 = 0; c4 < 8; ++c4) {
+                            const float4 m4 = apply_act_t<PRE>(make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1],
+                                                                           racc[pl * CP + c4 * 4 + 2], racc[pl * CP + c4 * 4 + 3]), a.slope);
+                            const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
+                            const float4 l = make_float4(m4.x - h.x, m4.y - h.y, m4.z - h.z, m4.w - h.w);
+                            *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
+                            *reinterpret_cast<float4*>(lo + (c4 * MIDP + row) * 4) = l;
+                        }
+                        fence_async_smem();
+                        mbar_arrive(m_full);
+                    }
+                }
+                mq += NT / CP;
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+                drain(n_g2);
+            }
+            // ---- epilogue: row `row` of the tile, this group's PPG pieces of 32 channels
+            const int t = j0 + row;
+            if (t < a.Tout) {
+#pragma unroll
+                for (int pl = 0; pl < PPG; ++pl) {
+                    const int co_l = co_tile * NT + (pl * NDG + dg) * CP;
+                    float* v = racc + pl * CP;
+                    if (a.bias) {
+#pragma unroll
+                        for (int i = 0; i < CP / 4; ++i) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + g * a.Cout_g + co_l) + i);
+                            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                        }
+                    }
+                    if (a.res) {
+                        const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
+#pragma unroll
+                        for (int i = 0; i < CP / 4; ++i) {
+                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                            v[4 * i] = r4.x + v[4 * i]; v[4 * i + 1] = r4.y + v[4 * i + 1];
+                            v[4 * i + 2] = r4.z + v[4 * i + 2]; v[4 * i + 3] = r4.w + v[4 * i + 3];
+                        }
+                    }
+                    if (a.out_nct) {
+                        float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
+#pragma unroll
+                        for (int i = 0; i < CP; ++i) yp[(long long)i * a.Tout] = v[i];
+                    } else {
+                        float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
+#pragma unroll
+                        for (int i = 0; i < CP / 4; ++i)
+                            *(reinterpret_cast<float4*>(yp) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+}  // namespace adec

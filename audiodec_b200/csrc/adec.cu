@@ -124,6 +124,7 @@ cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t
     return cudaLaunchKernelEx(&cfg, kern, a);
 }
 
+inline int TcpCfgStages(int NT) { return NT == 128 ? TcpCfg<128>::STAGES : NT == 64 ? TcpCfg<64>::STAGES : TcpCfg<32>::STAGES; }
 // persistent variant: one CTA per SM loops over (time tile, channel tile, stream) tiles
 typedef cudaError_t (*TcPersistFn)(const ConvArgs&, int, int, int, int, int, cudaStream_t);
 template <int NT, bool F, int PRE>
@@ -132,12 +133,17 @@ cudaError_t launch_tcp(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tile
     int dev = 0;
     cudaGetDevice(&dev);
     auto kern = tc_conv_persist_kernel<NT, F, PRE>;
+#ifdef ADEC_TIMELINE
+    constexpr int kMaxDyn = 227 * 1024 - 2048;
+#else
+    constexpr int kMaxDyn = 227 * 1024;
+#endif
     if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
-    if (smem_bytes > 227 * 1024) return cudaErrorInvalidConfiguration;
+    if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
     kern<<<n_ctas, TcCfg<NT>::THREADS, smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
     return cudaGetLastError();
 }
@@ -612,8 +618,9 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
                                                            (size_t)2 * TC_CP * (wrp + buf1_rows));
                 dim3 grid((Tout + TC_TT - 1) / TC_TT, op.G * op.n_co_tiles, rc.B);
                 if (h->persist_mask & op.tc->NT) {
-                    const size_t psmem = 256 + sizeof(float) * ((size_t)op.tc->stages * 2 * op.tc->KS * op.tc->NT + (size_t)4 * TC_CP * wrp +
-                                                                (op.fuse ? (size_t)2 * TC_CP * TC_MIDP : 0));
+                    const int pst = TcpCfgStages(op.tc->NT), pmb = op.tc->NT == 64 ? 2 : 1;
+                    const size_t psmem = 512 + sizeof(float) * ((size_t)pst * 2 * op.tc->KS * op.tc->NT + (size_t)4 * TC_CP * wrp +
+                                                                (op.fuse ? (size_t)pmb * 2 * TC_CP * TC_MIDP : 0));
                     const long long n_tiles = (long long)grid.x * grid.y * grid.z;
                     const int n_ctas = (int)std::min<long long>(n_tiles, h->n_sms);
                     e = op.tc->pfn(a, (int)grid.x, (int)grid.y, (int)n_tiles, n_ctas, (int)psmem, rc.stream);

@@ -95,7 +95,7 @@ struct TcCfg {
     static constexpr int MIN_CTAS = NT == 32 ? 2 : 1;
     static constexpr int CLUSTER = 1;                       // CTAs (adjacent time tiles) sharing one weight stream                       // co-resident CTAs hide each other's serial phases
     static constexpr int B_STAGE_FLOATS = 2 * TC_CP * NT;                   // hi | lo
-    static constexpr int NDG = NT == 128 ? 2 : 1;                           // drain warpgroups (each owns NT/NDG columns)
+    static constexpr int NDG = NT >= 64 ? 2 : 1;                            // drain warpgroups (each owns NT/NDG columns)
     static constexpr int NPROD = NT == 128 ? 128 : 256;                     // activation-producer threads
     static constexpr int DRAIN0 = (128 + NPROD) / 32;                       // first drain warp
     static constexpr int THREADS = 128 + NPROD + 128 * NDG;                 // warps 0-3 control, then producers, then drain

@@ -15,15 +15,20 @@
 
 namespace adec {
 
-constexpr int TCP_NPB = 4;    // TMEM partial buffers
+template <int NT> struct TcpCfg {
+    static constexpr int NPB = NT == 128 ? 4 : 8;          // TMEM partial buffers (NPB*NT <= 512 columns): how far the MMAs run ahead
+    static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128)
+    static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages
+};
 
 template <int NT, bool FUSE, int PRE>
 __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
     using Cfg = TcCfg<NT>;
-    constexpr int S = Cfg::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG;
-    constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0, MIDP = TC_MIDP, NPB = TCP_NPB;
+    constexpr int S = TcpCfg<NT>::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG;
+    constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0, MIDP = TC_MIDP, NPB = TcpCfg<NT>::NPB;
     constexpr int NCOL = NT / NDG;                       // accumulator registers per drain thread
     constexpr int PPG = NCOL / CP;                       // 32-column pieces owned by one drain group
+    constexpr int MB = TcpCfg<NT>::MB;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t TMEM_COLS = NPB * NT;
 
@@ -32,17 +37,17 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
     uint64_t* b_empty = b_full + S;                                // [S]   weights consumed
     uint64_t* w_full = b_empty + S;                                // [2]   window piece written
     uint64_t* w_empty = w_full + 2;                                // [2]   window piece consumed
-    uint64_t* m_full = w_empty + 2;                                // [1]   fused-intermediate piece written
-    uint64_t* m_empty = m_full + 1;                                // [1]   ... consumed
-    uint64_t* p_full = m_empty + 1;                                // [NPB] TMEM partial complete
+    uint64_t* m_full = w_empty + 2;                                // [MB]  fused-intermediate piece written
+    uint64_t* m_empty = m_full + 2;                                // [MB]  ... consumed
+    uint64_t* p_full = m_empty + 2;                                // [NPB] TMEM partial complete
     uint64_t* p_empty = p_full + NPB;                              // [NPB] TMEM partial drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + NPB);
-    float* bst = reinterpret_cast<float*>(smem_raw + 256);
+    float* bst = reinterpret_cast<float*>(smem_raw + 512);        // 32 barriers + the TMEM slot live in the first 512 B
     const int wrows = TT + (a.Ktaps - 1) * a.dil;
     const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
     float* wbuf0 = bst + S * BST;
     float* wbuf1 = wbuf0 + 2 * CP * wrp;
-    float* mbuf = wbuf1 + 2 * CP * wrp;                            // FUSE only: 2*CP*MIDP floats
+    float* mbuf = wbuf1 + 2 * CP * wrp;                            // FUSE only: MB x 2*CP*MIDP floats
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -52,7 +57,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], 2); }
-        mbar_init(m_full, 128); mbar_init(m_empty, 2);
+        for (int i = 0; i < MB; ++i) { mbar_init(&m_full[i], 128); mbar_init(&m_empty[i], 2); }
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
         mbar_fence_init();
     }
@@ -64,6 +69,14 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+#ifdef ADEC_TIMELINE
+    __shared__ unsigned tlp_[6][64];
+    __shared__ unsigned tlt_[8];
+    const long long tlp0_ = clock64();
+#define TLP(role, i) do { if (ti == 2 && (i) < 64) tlp_[role][(i)] = (unsigned)(clock64() - tlp0_); } while (0)
+#else
+#define TLP(role, i) do { } while (0)
+#endif
 
     if (warp == 0) {
         // ------------------------------------------------ weight producer
@@ -85,6 +98,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
         // ------------------------------------------------ MMA issuers (alternate groups)
         const int mw = warp - 1;
         int c = 0, wp = 0, mp = 0;
+        int ti = -1, c_tile0 = 0;
         const uint32_t b_lbo = (uint32_t)NT * 16u;
         const uint32_t wbuf0_u = smem_u32(wbuf0), wbuf1_u = smem_u32(wbuf1), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
         auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off) {
@@ -92,6 +106,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
             mbar_wait(&b_full[s], (c / S) & 1, 300);
             if (c >= NPB) mbar_wait(&p_empty[pb], ((c / NPB) - 1) & 1, 400);
             tc_fence_after();
+            if (lane == 0) TLP(1, c - c_tile0);
             const uint32_t b_hi = bst_u + (uint32_t)s * (BST * 4u);
             const uint32_t b_lo = b_hi + (uint32_t)CP * NT * 4u;
             const uint32_t acc = tmem + (uint32_t)pb * NT;
@@ -110,10 +125,12 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                               IDESC, 1u);
                 umma_commit(&b_empty[s]);
                 umma_commit(&p_full[pb]);
+                TLP(2, c - c_tile0);
             }
             __syncwarp();
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ++ti; c_tile0 = c;
             const uint32_t lbo1 = (uint32_t)wrp * 16u;
             for (int p = 0; p < a.n_pieces; ++p, ++wp) {
                 const int buf = wp & 1;
@@ -128,9 +145,11 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
             if (FUSE) {
                 const uint32_t lbo2 = (uint32_t)MIDP * 16u;
                 for (int p = 0; p < NT / CP; ++p, ++mp, ++c) {
-                    mbar_wait(m_full, mp & 1, 250);
-                    if ((c & 1) == mw) issue_group(mbuf_u, mbuf_u + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
-                    if (elect_one()) umma_commit(m_empty);
+                    const int mb = mp % MB;
+                    mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
+                    const uint32_t m_hi = mbuf_u + (uint32_t)mb * (2u * CP * MIDP * 4u);
+                    if ((c & 1) == mw) issue_group(m_hi, m_hi + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
+                    if (elect_one()) umma_commit(&m_empty[mb]);
                     __syncwarp();
                 }
             }
@@ -142,7 +161,9 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
         constexpr int RPP = NPROD / 8;
         constexpr int UNR = 6;
         const int c4 = pt & 7, m0 = pt >> 3;
+        int ti = -1;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ++ti;
             const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
             const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
             const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
@@ -220,6 +241,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                 }
                 fence_async_smem();
                 mbar_arrive(&w_full[buf]);
+                if (pt == 0) TLP(3, p);
             }
             // ---- new causal state (conv_layer.py:155)
             if (xt == (a.Tout - 1) / TT && co_tile == 0 && g < a.st_groups && a.P > 0) {
@@ -255,12 +277,14 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
         // Column ownership: piece pl of group dg is 32-column piece (pl*NDG + dg), so that consecutive intermediate
         // pieces alternate between the groups and every group meets every m_empty phase in order.
         float racc[NCOL];
-        int c = 0, m_seen = 0, mq = 0;
+        int c = 0, mq = 0, ti = -1, c_tile0 = 0;
+        int m_seen[2] = {0, 0};
         auto drain = [&](int ngroups) {
             for (int gi = 0; gi < ngroups; ++gi, ++c) {
                 const int pb = c % NPB;
                 mbar_wait(&p_full[pb], (c / NPB) & 1, 600);
                 tc_fence_after();
+                if (tid == DRAIN0 * 32) TLP(4, c - c_tile0);
 #pragma unroll
                 for (int pl = 0; pl < PPG; ++pl) {
                     const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)(pl * NDG + dg) * CP;
@@ -276,37 +300,48 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                 }
                 tc_fence_before();
                 mbar_arrive(&p_empty[pb]);
+                if (tid == DRAIN0 * 32) TLP(5, c - c_tile0);
             }
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            ++ti; c_tile0 = c;
+#ifdef ADEC_TIMELINE
+            if (tid == DRAIN0 * 32 && ti >= 1 && ti <= 4) tlt_[ti] = (unsigned)(clock64() - tlp0_);
+#endif
             const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
             const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
 #pragma unroll
             for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
             drain(n_g1);
             if (FUSE) {
-                // intermediate pieces in consumption order 0,1,2,...: piece q is written by group q % NDG.  The single
-                // buffer is free again once piece q-1 was consumed = completion #(mq+q-1) of m_empty; every thread walks
-                // through all completions in order.
+                // activation first (registers only), so that it overlaps the wait for a free intermediate buffer
+#pragma unroll
+                for (int i = 0; i < NCOL; i += 4) {
+                    const float4 m4 = apply_act_t<PRE>(make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]), a.slope);
+                    racc[i] = m4.x; racc[i + 1] = m4.y; racc[i + 2] = m4.z; racc[i + 3] = m4.w;
+                }
+                // intermediate pieces in consumption order 0,1,2,...: piece q is written by group q % NDG into buffer
+                // Q % MB (Q = running piece index), which is free once piece Q-MB was consumed = completion #(Q/MB - 1) of
+                // that buffer's m_empty.  Every thread walks through all completions of both buffers in order.
 #pragma unroll
                 for (int q = 0; q < NT / CP; ++q) {
-                    const int need = mq + q;                 // completions that must have happened before piece q is written
-                    while (m_seen < need) { mbar_wait(m_empty, m_seen & 1, 700); ++m_seen; }
+                    const int Q = mq + q, mb = Q % MB;
+                    while (m_seen[mb] < Q / MB) { mbar_wait(&m_empty[mb], m_seen[mb] & 1, 700); ++m_seen[mb]; }
                     if (q % NDG == dg) {
                         const int pl = q / NDG;
-                        float* hi = mbuf;
+                        float* hi = mbuf + mb * (2 * CP * MIDP);
                         float* lo = hi + CP * MIDP;
 #pragma unroll
                         for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 m4 = apply_act_t<PRE>(make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1],
-                                                                           racc[pl * CP + c4 * 4 + 2], racc[pl * CP + c4 * 4 + 3]), a.slope);
+                            const float4 m4 = make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1], racc[pl * CP + c4 * 4 + 2],
+                                                          racc[pl * CP + c4 * 4 + 3]);
                             const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
                             const float4 l = make_float4(m4.x - h.x, m4.y - h.y, m4.z - h.z, m4.w - h.w);
                             *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
                             *reinterpret_cast<float4*>(lo + (c4 * MIDP + row) * 4) = l;
                         }
                         fence_async_smem();
-                        mbar_arrive(m_full);
+                        mbar_arrive(&m_full[mb]);
                     }
                 }
                 mq += NT / CP;
@@ -330,11 +365,13 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                     }
                     if (a.res) {
                         const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
+                        float4 r4[CP / 4];
+#pragma unroll
+                        for (int i = 0; i < CP / 4; ++i) r4[i] = __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
 #pragma unroll
                         for (int i = 0; i < CP / 4; ++i) {
-                            const float4 r4 = __ldg(reinterpret_cast<const float4*>(rp) + i);
-                            v[4 * i] = r4.x + v[4 * i]; v[4 * i + 1] = r4.y + v[4 * i + 1];
-                            v[4 * i + 2] = r4.z + v[4 * i + 2]; v[4 * i + 3] = r4.w + v[4 * i + 3];
+                            v[4 * i] = r4[i].x + v[4 * i]; v[4 * i + 1] = r4[i].y + v[4 * i + 1];
+                            v[4 * i + 2] = r4[i].z + v[4 * i + 2]; v[4 * i + 3] = r4[i].w + v[4 * i + 3];
                         }
                     }
                     if (a.out_nct) {
@@ -353,6 +390,16 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
     }
     tc_fence_before();
     __syncthreads();
+#ifdef ADEC_TIMELINE
+    if (tid == 0 && blockIdx.x == 1) {
+        const int ng = n_g1 + n_g2 < 64 ? n_g1 + n_g2 : 64;
+        printf("PTIMELINE NT=%d fuse=%d groups=%d pieces=%d tile starts(drain) t1=%u t2=%u t3=%u t4=%u end=%u\n", NT, (int)FUSE, n_g1 + n_g2,
+               a.n_pieces, tlt_[1], tlt_[2], tlt_[3], tlt_[4], (unsigned)(clock64() - tlp0_));
+        for (int i = 0; i < ng; ++i)
+            printf(" g%02d mma ready %7u issued %7u | drain got %7u done %7u\n", i, tlp_[1][i], tlp_[2][i], tlp_[4][i], tlp_[5][i]);
+        for (int i = 0; i < a.n_pieces && i < 64; ++i) printf(" piece %d produced %7u\n", i, tlp_[3][i]);
+    }
+#endif
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 

@@ -144,7 +144,7 @@ cudaError_t launch_tcp(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tile
         configured[dev] = true;
     }
     if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
-    kern<<<n_ctas, TcCfg<NT>::THREADS, smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
+    kern<<<n_ctas, TcpCfg<NT>::THREADS, smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
     return cudaGetLastError();
 }
 
@@ -154,7 +154,7 @@ struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; ConvLaunchFn fn; Tc
     ADEC_TC1(NT, true, ACT_ELU), ADEC_TC1(NT, false, ACT_NONE), ADEC_TC1(NT, false, ACT_ELU), ADEC_TC1(NT, false, ACT_LRELU), \
     ADEC_TC1(NT, false, ACT_NORM)
 const TcKernelCfg kTcKernels[] = {ADEC_TC(128), ADEC_TC(64), ADEC_TC(32)};
-constexpr int kTcMaxFuse = 128;    // residual units wider than this run as two launches on the tensor-core path
+int kTcMaxFuse = 128;    // residual units wider than this run as two launches on the tensor-core path (ADEC_TC_MAXFUSE)
 
 const TcKernelCfg* find_tc_kernel(int NT, bool fuse, int pre) {
     for (const auto& k : kTcKernels)
@@ -964,6 +964,7 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     h->device = device;
     if (const char* pth = getenv("ADEC_CONV_PATH")) h->use_tc = strcmp(pth, "ffma") != 0;
     if (const char* pm = getenv("ADEC_TC_PERSIST")) h->persist_mask = atoi(pm);
+    if (const char* mf = getenv("ADEC_TC_MAXFUSE")) kTcMaxFuse = atoi(mf);
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     DeviceGuard dg(device);
     if (cudaMalloc((void**)&h->d_err, sizeof(int)) != cudaSuccess || cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) {

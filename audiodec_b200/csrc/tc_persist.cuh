@@ -19,15 +19,19 @@ template <int NT> struct TcpCfg {
     static constexpr int NPB = NT == 128 ? 4 : 8;          // TMEM partial buffers (NPB*NT <= 512 columns): how far the MMAs run ahead
     static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128)
     static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages
+    static constexpr int NDG = NT == 32 ? 2 : TcCfg<NT>::NDG;          // drain groups; at NT=32 each owns HALF a 32-column piece
+    static constexpr int THREADS = 128 + TcCfg<NT>::NPROD + 128 * NDG;
 };
 
 template <int NT, bool FUSE, int PRE>
-__global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
+__global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
     using Cfg = TcCfg<NT>;
-    constexpr int S = TcpCfg<NT>::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG;
+    constexpr int S = TcpCfg<NT>::STAGES, BST = Cfg::B_STAGE_FLOATS, CP = TC_CP, TT = TC_TT, NDG = TcpCfg<NT>::NDG;
     constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0, MIDP = TC_MIDP, NPB = TcpCfg<NT>::NPB;
     constexpr int NCOL = NT / NDG;                       // accumulator registers per drain thread
-    constexpr int PPG = NCOL / CP;                       // 32-column pieces owned by one drain group
+    constexpr bool HALF = NCOL < CP;                     // NT=32: a drain group owns 16 of the piece's 32 columns
+    constexpr int PPG = HALF ? 1 : NCOL / CP;            // 32-column pieces (or half pieces) owned by one drain group
+    constexpr int UC = HALF ? NCOL : CP;                 // columns per owned unit
     constexpr int MB = TcpCfg<NT>::MB;
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t TMEM_COLS = NPB * NT;
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], 2); }
-        for (int i = 0; i < MB; ++i) { mbar_init(&m_full[i], 128); mbar_init(&m_empty[i], 2); }
+        for (int i = 0; i < MB; ++i) { mbar_init(&m_full[i], HALF ? 256 : 128); mbar_init(&m_empty[i], 2); }
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
         mbar_fence_init();
     }
@@ -285,17 +289,25 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                 mbar_wait(&p_full[pb], (c / NPB) & 1, 600);
                 tc_fence_after();
                 if (tid == DRAIN0 * 32) TLP(4, c - c_tile0);
-#pragma unroll
-                for (int pl = 0; pl < PPG; ++pl) {
-                    const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)(pl * NDG + dg) * CP;
-                    uint32_t r0[16], r1[16];
-                    tmem_ld16(taddr, r0);
-                    tmem_ld16(taddr + 16, r1);
+                if (HALF) {
+                    uint32_t r0[16];
+                    tmem_ld16(tmem + lane_base + (uint32_t)pb * NT + (uint32_t)dg * UC, r0);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        racc[pl * CP + i] = __fadd_rn(racc[pl * CP + i], __uint_as_float(r0[i]));
-                        racc[pl * CP + 16 + i] = __fadd_rn(racc[pl * CP + 16 + i], __uint_as_float(r1[i]));
+                    for (int i = 0; i < 16; ++i) racc[i] = __fadd_rn(racc[i], __uint_as_float(r0[i]));
+                } else {
+#pragma unroll
+                    for (int pl = 0; pl < PPG; ++pl) {
+                        const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)(pl * NDG + dg) * CP;
+                        uint32_t r0[16], r1[16];
+                        tmem_ld16(taddr, r0);
+                        tmem_ld16(taddr + 16, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            racc[pl * UC + i] = __fadd_rn(racc[pl * UC + i], __uint_as_float(r0[i]));
+                            racc[pl * UC + 16 + i] = __fadd_rn(racc[pl * UC + 16 + i], __uint_as_float(r1[i]));
+                        }
                     }
                 }
                 tc_fence_before();
@@ -327,14 +339,15 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                 for (int q = 0; q < NT / CP; ++q) {
                     const int Q = mq + q, mb = Q % MB;
                     while (m_seen[mb] < Q / MB) { mbar_wait(&m_empty[mb], m_seen[mb] & 1, 700); ++m_seen[mb]; }
-                    if (q % NDG == dg) {
-                        const int pl = q / NDG;
+                    if (HALF || q % NDG == dg) {
+                        const int pl = HALF ? 0 : q / NDG;
                         float* hi = mbuf + mb * (2 * CP * MIDP);
                         float* lo = hi + CP * MIDP;
 #pragma unroll
-                        for (int c4 = 0; c4 < 8; ++c4) {
-                            const float4 m4 = make_float4(racc[pl * CP + c4 * 4], racc[pl * CP + c4 * 4 + 1], racc[pl * CP + c4 * 4 + 2],
-                                                          racc[pl * CP + c4 * 4 + 3]);
+                        for (int u = 0; u < UC / 4; ++u) {
+                            const int c4 = HALF ? dg * (UC / 4) + u : u;       // 16-byte channel column inside the 32-channel piece
+                            const float4 m4 = make_float4(racc[pl * UC + u * 4], racc[pl * UC + u * 4 + 1], racc[pl * UC + u * 4 + 2],
+                                                          racc[pl * UC + u * 4 + 3]);
                             const float4 h = make_float4(tf32_rna(m4.x), tf32_rna(m4.y), tf32_rna(m4.z), tf32_rna(m4.w));
                             const float4 l = make_float4(m4.x - h.x, m4.y - h.y, m4.z - h.z, m4.w - h.w);
                             *reinterpret_cast<float4*>(hi + (c4 * MIDP + row) * 4) = h;
@@ -354,22 +367,22 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
             if (t < a.Tout) {
 #pragma unroll
                 for (int pl = 0; pl < PPG; ++pl) {
-                    const int co_l = co_tile * NT + (pl * NDG + dg) * CP;
-                    float* v = racc + pl * CP;
+                    const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
+                    float* v = racc + pl * UC;
                     if (a.bias) {
 #pragma unroll
-                        for (int i = 0; i < CP / 4; ++i) {
+                        for (int i = 0; i < UC / 4; ++i) {
                             const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + g * a.Cout_g + co_l) + i);
                             v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
                         }
                     }
                     if (a.res) {
                         const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
-                        float4 r4[CP / 4];
+                        float4 r4[UC / 4];
 #pragma unroll
-                        for (int i = 0; i < CP / 4; ++i) r4[i] = __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
+                        for (int i = 0; i < UC / 4; ++i) r4[i] = __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
 #pragma unroll
-                        for (int i = 0; i < CP / 4; ++i) {
+                        for (int i = 0; i < UC / 4; ++i) {
                             v[4 * i] = r4[i].x + v[4 * i]; v[4 * i + 1] = r4[i].y + v[4 * i + 1];
                             v[4 * i + 2] = r4[i].z + v[4 * i + 2]; v[4 * i + 3] = r4[i].w + v[4 * i + 3];
                         }
@@ -377,11 +390,11 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, 1) tc_conv_persist_kernel(
                     if (a.out_nct) {
                         float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
 #pragma unroll
-                        for (int i = 0; i < CP; ++i) yp[(long long)i * a.Tout] = v[i];
+                        for (int i = 0; i < UC; ++i) yp[(long long)i * a.Tout] = v[i];
                     } else {
                         float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
 #pragma unroll
-                        for (int i = 0; i < CP / 4; ++i)
+                        for (int i = 0; i < UC / 4; ++i)
                             *(reinterpret_cast<float4*>(yp) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
                 }

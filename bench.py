@@ -155,6 +155,11 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # pre-warm: clocks / power state settle over the first ~second of load; these steps are not counted in W
+    t_pre = time.time()
+    while time.time() - t_pre < 1.5:
+        step(0)
+        torch.cuda.synchronize(dev)
     for i in range(args.warmup):
         step(i)
     barrier()
@@ -207,6 +212,10 @@ def run_ours(args):
             a[1] += ms
         tot = sum(v[1] for v in agg.values())
         top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+        if args.breakdown:
+            for k, v in agg.items():
+                print(f"  {k:44s} {v[1] / v[0]:8.3f} ms  {v[2] / (v[1] / v[0]) / 1e6:8.1f} GB/s(alg)", file=sys.stderr)
+            print(f"  sum of launches per step: {tot / 2:.3f} ms", file=sys.stderr)
         dname, (dn, dms, dbytes) = top[0]
         prof = {"kernel": dname, "launch_ms": dms / dn, "alg_bytes_per_launch": dbytes, "share_of_step": dms / tot,
                 "conv_kernels_share_of_step": sum(v[1] for k, v in agg.items() if "res_units" in k or ".conv" in k or "project" in k
@@ -357,6 +366,7 @@ def main():
     ap.add_argument("--workload", default="symad", choices=["symad", "v1"])
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-utts", type=int, default=4)
+    ap.add_argument("--breakdown", action="store_true", help="print per-launch CUDA-event times to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -268,10 +268,11 @@ class HiFiGANStreamGenerator(_StreamGeneratorBase):
         return y
 
 
-def codec_host(encoder: SymADStreamGenerator, decoder, x_host: torch.Tensor, want_idx=True):
+def codec_host(encoder: SymADStreamGenerator, decoder, x_host: torch.Tensor, want_idx=True, reuse_buffers=False):
     """Whole path on HOST buffers through ``adec_codec_host`` (H2D + encode + quantize + lookup + decode +
     D2H), i.e. what demoFile.py:55-62 does around the four calls.  x_host: (B,1,T) float32 CPU tensor
-    (pinned for full PCIe speed).  Returns (idx (Nq,B,F) int64 CPU or None, y (B,1,F*hop) float32 CPU)."""
+    (pinned for full PCIe speed).  With reuse_buffers the returned tensors are views of cached pinned buffers that
+    the next call overwrites.  Returns (idx (Nq,B,F) int64 CPU or None, y (B,1,F*hop) float32 CPU)."""
     encoder._ready(), decoder._ready()
     assert x_host.device.type == "cpu" and x_host.dtype == torch.float32 and x_host.is_contiguous()
     b, _, t = x_host.shape
@@ -282,8 +283,18 @@ def codec_host(encoder: SymADStreamGenerator, decoder, x_host: torch.Tensor, wan
     f = lib.adec_frames_for(encoder._h, t)
     hop = lib.adec_hop_length(decoder._h)
     pin = x_host.is_pinned()
-    idx = torch.empty(encoder.codebook_num, b, f, dtype=torch.int64, pin_memory=pin) if want_idx else None
-    y = torch.empty(b, 1, f * hop, dtype=torch.float32, pin_memory=pin)
+    # page-locked result buffers are expensive to create (cudaHostAlloc): keep one set per shape and hand out views;
+    # pass reuse_buffers=False to get fresh tensors that the next call will not overwrite
+    cache = encoder.__dict__.setdefault("_host_out", {})
+    key = (b, f, hop, pin, want_idx)
+    if reuse_buffers and key in cache:
+        idx, y = cache[key]
+    else:
+        idx = torch.empty(encoder.codebook_num, b, f, dtype=torch.int64, pin_memory=pin) if want_idx else None
+        y = torch.empty(b, 1, f * hop, dtype=torch.float32, pin_memory=pin)
+        if reuse_buffers:
+            cache.clear()
+            cache[key] = (idx, y)
     _check(lib.adec_codec_host(encoder._h, decoder._h, _ptr(x_host), b, t, _ptr(idx) if want_idx else None,
                                _ptr(y), encoder._stream()), encoder._h)
     return idx, y

@@ -1094,7 +1094,7 @@ int adec_quantize(adec_handle* h, const float* z, int B, int F, int64_t* idx, vo
     RvqArgs a{};
     a.z = z; a.B = B; a.F = F; a.nq = h->cfg.codebook_num; a.embed = h->d_embed; a.e2 = h->d_e2; a.idx = (long long*)idx;
     const long long nfr = (long long)B * F;
-    rvq_kernel<64, 8><<<(unsigned)((nfr + RVQ_FRAMES - 1) / RVQ_FRAMES), RVQ_THREADS, 0, (cudaStream_t)stream>>>(a);
+    rvq_kernel<64, 4><<<(unsigned)((nfr + RVQ_FRAMES - 1) / RVQ_FRAMES), RVQ_THREADS, 0, (cudaStream_t)stream>>>(a);
     CK(h, cudaGetLastError());
     ++h->launches;
     return 0;

@@ -495,28 +495,28 @@ struct RvqArgs {
     long long* idx;        // (nq, B, F) flat indices (+ N*i)
 };
 
-constexpr int RVQ_FRAMES = 8;     // frames per block
-constexpr int RVQ_THREADS = 128;
+constexpr int RVQ_FRAMES = 32;    // frames per block: the 256 KB stage codebook is streamed from L2 once per 32 frames
+constexpr int RVQ_THREADS = 256;
 
 template <int D, int NPT>   // codebook size N = RVQ_THREADS * NPT
 __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
-    constexpr int N = RVQ_THREADS * NPT, FR = RVQ_FRAMES;
+    constexpr int N = RVQ_THREADS * NPT, FR = RVQ_FRAMES, NW = RVQ_THREADS / 32;
     static_assert(D % 32 == 0, "D must be a multiple of 32");
-    __shared__ float r[FR][D];          // residuals
+    __shared__ __align__(16) float r[FR][D];          // residuals
     __shared__ float x2[FR];
-    __shared__ float wv[FR][RVQ_THREADS / 32];
-    __shared__ int wi[FR][RVQ_THREADS / 32];
+    __shared__ float wv[FR][NW];
+    __shared__ int wi[FR][NW];
     __shared__ int best[FR];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long nfr = (long long)a.B * a.F;
     const long long f0 = (long long)blockIdx.x * FR;
     for (int i = tid; i < FR * D; i += RVQ_THREADS) {
-        const int f = i / D, k = i - f * D;
+        const int f = i % FR, k = i / FR;            // consecutive threads -> consecutive frames: coalesced reads of z (B,D,F)
         const long long fr = f0 + f;
         float v = 0.f;
         if (fr < nfr) {
             const long long bb = fr / a.F, ff = fr - bb * a.F;
-            v = a.z[(bb * D + k) * a.F + ff];       // quantizer.py:43 z.transpose(2,1)
+            v = a.z[(bb * D + k) * a.F + ff];        // quantizer.py:43 z.transpose(2,1)
         }
         r[f][k] = v;
     }
@@ -545,52 +545,61 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
             }
             x2[tid] = s;
         }
-        // dot2[c] = sum_k (2 r_k) * E[k][c], k ascending, fused multiply-add (MKL sgemm order)
-        float acc[FR][NPT];
-#pragma unroll
-        for (int f = 0; f < FR; ++f)
-#pragma unroll
-            for (int m = 0; m < NPT; ++m) acc[f][m] = 0.f;
-#pragma unroll 4
-        for (int k = 0; k < D; ++k) {
-            float e[NPT];
-#pragma unroll
-            for (int m = 0; m < NPT; ++m) e[m] = __ldg(E + (long long)k * N + tid + m * RVQ_THREADS);
-#pragma unroll
-            for (int f = 0; f < FR; ++f) {
-                const float rk = 2.0f * r[f][k];
-#pragma unroll
-                for (int m = 0; m < NPT; ++m) acc[f][m] = fmaf(rk, e[m], acc[f][m]);
-            }
-        }
-        __syncthreads();   // x2 visible
+        // dot2[c] = sum_k (2 r_k) * E[k][c], k ascending, one fused multiply-add chain per output (MKL sgemm order).
+        // Frames are processed in two halves of 16 to bound registers; each codebook element is loaded once per half.
         float e2v[NPT];
 #pragma unroll
         for (int m = 0; m < NPT; ++m) e2v[m] = __ldg(a.e2 + (long long)st * N + tid + m * RVQ_THREADS);
+        __syncthreads();   // x2 visible
+#pragma unroll 1
+        for (int fh = 0; fh < FR; fh += 16) {
+            float acc[16][NPT];
 #pragma unroll
-        for (int f = 0; f < FR; ++f) {
-            // dist = (x2 - dot2) + e2 ; index = first arg-max of -dist  (vq_module.py:93-98)
-            float bv = 0.f;
-            int bi = 0;
+            for (int f = 0; f < 16; ++f)
 #pragma unroll
-            for (int m = 0; m < NPT; ++m) {
-                const float nd = -__fadd_rn(__fsub_rn(x2[f], acc[f][m]), e2v[m]);
-                if (m == 0 || nd > bv) { bv = nd; bi = tid + m * RVQ_THREADS; }
+                for (int m = 0; m < NPT; ++m) acc[f][m] = 0.f;
+#pragma unroll 1
+            for (int k = 0; k < D; k += 4) {
+                float e[4][NPT];
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int m = 0; m < NPT; ++m) e[kk][m] = __ldg(E + (long long)(k + kk) * N + tid + m * RVQ_THREADS);
+#pragma unroll
+                for (int f = 0; f < 16; ++f) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(&r[fh + f][k]);
+                    const float rk[4] = {2.0f * r4.x, 2.0f * r4.y, 2.0f * r4.z, 2.0f * r4.w};
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                        for (int m = 0; m < NPT; ++m) acc[f][m] = fmaf(rk[kk], e[kk][m], acc[f][m]);
+                }
             }
 #pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
-                const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-                if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+            for (int f = 0; f < 16; ++f) {
+                // dist = (x2 - dot2) + e2 ; index = first arg-max of -dist  (vq_module.py:93-98)
+                float bv = 0.f;
+                int bi = 0;
+#pragma unroll
+                for (int m = 0; m < NPT; ++m) {
+                    const float nd = -__fadd_rn(__fsub_rn(x2[fh + f], acc[f][m]), e2v[m]);
+                    if (m == 0 || nd > bv) { bv = nd; bi = tid + m * RVQ_THREADS; }
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, bv, off);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+                }
+                if (lane == 0) { wv[fh + f][warp] = bv; wi[fh + f][warp] = bi; }
             }
-            if (lane == 0) { wv[f][warp] = bv; wi[f][warp] = bi; }
         }
         __syncthreads();
         if (tid < FR) {
             float bv = wv[tid][0];
             int bi = wi[tid][0];
 #pragma unroll
-            for (int w = 1; w < RVQ_THREADS / 32; ++w) {
+            for (int w = 1; w < NW; ++w) {
                 const float ov = wv[tid][w];
                 const int oi = wi[tid][w];
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }

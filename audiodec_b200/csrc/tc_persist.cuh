@@ -18,7 +18,7 @@ namespace adec {
 template <int NT> struct TcpCfg {
     static constexpr int NPB = NT == 128 ? 4 : 8;          // TMEM partial buffers (NPB*NT <= 512 columns): how far the MMAs run ahead
     static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128)
-    static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages
+    static constexpr int STAGES = NT == 32 ? 8 : TcCfg<NT>::STAGES;   // weight stages (8 KB each at NT=32: enough in flight to cover the L2 refill latency)
     static constexpr int NDG = NT == 32 ? 2 : TcCfg<NT>::NDG;          // drain groups; at NT=32 each owns HALF a 32-column piece
     static constexpr int THREADS = 128 + TcCfg<NT>::NPROD + 128 * NDG;
 };
@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
     uint64_t* p_full = m_empty + 2;                                // [NPB] TMEM partial complete
     uint64_t* p_empty = p_full + NPB;                              // [NPB] TMEM partial drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + NPB);
-    float* bst = reinterpret_cast<float*>(smem_raw + 512);        // 32 barriers + the TMEM slot live in the first 512 B
+    float* bst = reinterpret_cast<float*>(smem_raw + 512);        // up to 40 barriers + the TMEM slot live in the first 512 B
     const int wrows = TT + (a.Ktaps - 1) * a.dil;
     const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
     float* wbuf0 = bst + S * BST;

@@ -175,3 +175,14 @@ def test_no_cpu_fallback(symad_sd):
         g.to("cpu")
     with pytest.raises(RuntimeError):
         g.encode(torch.zeros(1, 1, 300))
+
+
+def test_codec_host_path_matches_device_path(golden_dir, symad_sd):
+    """adec_codec_host (host buffers: H2D + four calls + D2H) == the four calls on device tensors == golden."""
+    from audiodec_b200.codec import codec_host
+    g = np.load(os.path.join(golden_dir, "symad_batch3.npz"))
+    tx, rx, dec, _ = _codec(symad_sd)
+    idx_h, y_h = codec_host(tx, dec, torch.from_numpy(g["x"]).pin_memory())
+    assert tuple(idx_h.shape) == (8, 3, 20) and not idx_h.is_cuda and not y_h.is_cuda
+    np.testing.assert_array_equal(idx_h.numpy(), g["idx"])
+    np.testing.assert_allclose(y_h.numpy(), g["y"], atol=WAVE_TOL)

@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaudiodec_b200.so")
+LIB_PATH = os.environ.get("ADEC_LIB_PATH") or os.path.join(_HERE, "lib", "libaudiodec_b200.so")   # override: A/B experiments only
 MAX_STAGES = 8
 
 c_int, c_float, c_void_p, c_char_p = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_char_p

@@ -618,7 +618,7 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
                                                            (size_t)2 * TC_CP * (wrp + buf1_rows));
                 dim3 grid((Tout + TC_TT - 1) / TC_TT, op.G * op.n_co_tiles, rc.B);
                 if (h->persist_mask & op.tc->NT) {
-                    const int pst = TcpCfgStages(op.tc->NT), pmb = op.tc->NT == 64 ? 2 : 1;
+                    const int pst = TcpCfgStages(op.tc->NT), pmb = op.tc->NT == 128 ? TcpCfg<128>::MB : op.tc->NT == 64 ? TcpCfg<64>::MB : TcpCfg<32>::MB;
                     const size_t psmem = 512 + sizeof(float) * ((size_t)pst * 2 * op.tc->KS * op.tc->NT + (size_t)4 * TC_CP * wrp +
                                                                 (op.fuse ? (size_t)pmb * 2 * TC_CP * TC_MIDP : 0));
                     const long long n_tiles = (long long)grid.x * grid.y * grid.z;

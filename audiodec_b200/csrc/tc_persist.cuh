@@ -17,8 +17,13 @@ namespace adec {
 
 template <int NT> struct TcpCfg {
     static constexpr int NPB = NT == 128 ? 4 : 8;          // TMEM partial buffers (NPB*NT <= 512 columns): how far the MMAs run ahead
+#ifdef ADEC_ALT_NT64
+    static constexpr int MB = 1;
+    static constexpr int STAGES = NT == 64 ? 6 : TcCfg<NT>::STAGES;
+#else
     static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128)
-    static constexpr int STAGES = NT == 32 ? 8 : TcCfg<NT>::STAGES;   // weight stages (8 KB each at NT=32: enough in flight to cover the L2 refill latency)
+    static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages (8 stages at NT=32 measured no faster)
+#endif
     static constexpr int NDG = NT == 32 ? 2 : TcCfg<NT>::NDG;          // drain groups; at NT=32 each owns HALF a 32-column piece
     static constexpr int THREADS = 128 + TcCfg<NT>::NPROD + 128 * NDG;
 };
@@ -281,6 +286,8 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
         // Column ownership: piece pl of group dg is 32-column piece (pl*NDG + dg), so that consecutive intermediate
         // pieces alternate between the groups and every group meets every m_empty phase in order.
         float racc[NCOL];
+        constexpr bool PREFETCH_RES = FUSE && NT <= 64;     // registers permitting
+        float4 rpre[PREFETCH_RES ? PPG : 1][UC / 4];
         int c = 0, mq = 0, ti = -1, c_tile0 = 0;
         int m_seen[2] = {0, 0};
         auto drain = [&](int ngroups) {
@@ -360,6 +367,16 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 mq += NT / CP;
 #pragma unroll
                 for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+                if (PREFETCH_RES && a.res && j0 + row < a.Tout) {
+                    // the skip tensor's rows are known now: fetch them while the 1x1 conv's MMAs run
+#pragma unroll
+                    for (int pl = 0; pl < PPG; ++pl) {
+                        const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
+                        const float* rp = a.res + (long long)b * a.res_bs + (long long)(j0 + row) * a.ldr + g * a.r_goff + co_l;
+#pragma unroll
+                        for (int i = 0; i < UC / 4; ++i) rpre[pl][i] = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                    }
+                }
                 drain(n_g2);
             }
             // ---- epilogue: row `row` of the tile, this group's PPG pieces of 32 channels
@@ -380,7 +397,8 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                         const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
                         float4 r4[UC / 4];
 #pragma unroll
-                        for (int i = 0; i < UC / 4; ++i) r4[i] = __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
+                        for (int i = 0; i < UC / 4; ++i)
+                            r4[i] = PREFETCH_RES ? rpre[PREFETCH_RES ? pl : 0][i] : __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
 #pragma unroll
                         for (int i = 0; i < UC / 4; ++i) {
                             v[4 * i] = r4[i].x + v[4 * i]; v[4 * i + 1] = r4[i].y + v[4 * i + 1];

@@ -264,7 +264,7 @@ def run_ours(args):
                 "api": "audiodec_b200.codec.codec_host -> adec_codec_host (pinned host buffers, per GPU)"},
         "roofline": {"bound": "hbm", "achieved": k_achieved, "peak": peak, "unit": "GB/s", "frac": k_achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": (("tc_conv_kernel (tcgen05 3xTF32)" if conv_path != "ffma" else "conv_gemm_kernel (fp32 FFMA)")
+                     "kernel": (("tc_conv_persist_kernel (tcgen05 3xTF32)" if conv_path != "ffma" else "conv_gemm_kernel (fp32 FFMA)")
                                 + " launch of " + (prof["kernel"] if prof else "?")),
                      "kernel_launch_ms": prof["launch_ms"] if prof else None,
                      "kernel_alg_bytes_per_launch": prof["alg_bytes_per_launch"] if prof else None,

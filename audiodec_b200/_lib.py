@@ -34,6 +34,8 @@ class AdecConfig(ctypes.Structure):
         ("negative_slope", c_float),
         ("use_weight_norm", c_int),
         ("has_stats", c_int),
+        ("codec_activate", c_int),
+        ("n_resblocks", c_int), ("resblock_kernel_sizes", _I8),
     ]
 
 

@@ -149,8 +149,8 @@ class SymADStreamGenerator(_StreamGeneratorBase):
                  nonlinear_activation_params={}, use_weight_norm=False):
         super().__init__()
         assert mode == "causal", f"Mode {mode} does not support streaming!"       # models/utils.py:13-15
-        if codec != "audiodec":
-            raise NotImplementedError(f"Codec ({codec}) is not supported!")          # AudioDec.py:59-60 (symAAD: next)
+        if codec not in ("audiodec", "activate_audiodec"):
+            raise NotImplementedError(f"Codec ({codec}) is not supported!")          # AudioDec.py:53-60
         if projector != "conv1d" or quantier != "residual_vq":
             raise NotImplementedError("only projector='conv1d', quantier='residual_vq' are built")
         if nonlinear_activation != "ELU" or nonlinear_activation_params:
@@ -165,6 +165,7 @@ class SymADStreamGenerator(_StreamGeneratorBase):
         _fill(c.enc_ratios, enc_ratios), _fill(c.enc_strides, enc_strides)
         _fill(c.dec_ratios, dec_ratios), _fill(c.dec_strides, dec_strides)
         c.use_weight_norm = int(use_weight_norm)
+        c.codec_activate = int(codec == "activate_audiodec")
         self.input_channels = input_channels
         self.code_dim, self.codebook_num = code_dim, codebook_num
 
@@ -236,8 +237,11 @@ class HiFiGANStreamGenerator(_StreamGeneratorBase):
         assert kernel_size % 2 == 1, "Kernel size must be odd number."               # HiFiGAN.py:73-75
         assert len(upsample_scales) == len(upsample_kernel_sizes)
         assert len(resblock_dilations) == len(resblock_kernel_sizes)
-        if not (len(resblock_kernel_sizes) == 1 and groups > 1):
-            raise NotImplementedError("only the MultiGroupConv1d generator (AD v1/v2 style) is built; v0 is 'next'")
+        multi_group = len(resblock_kernel_sizes) == 1 and groups > 1              # HiFiGAN.py:78-81
+        if not multi_group:
+            # MultiReceptiveField (AD v0): one residual block per kernel size, outputs averaged (multi_fusion.py:23-79)
+            if groups != 1 or any(list(d) != list(resblock_dilations[0]) for d in resblock_dilations):
+                raise NotImplementedError("MultiReceptiveField is built for groups=1 and identical dilation lists")
         if nonlinear_activation != "LeakyReLU" or not use_additional_convs or not bias:
             raise NotImplementedError("only LeakyReLU + additional convs + bias is built")
         c = self._cfg
@@ -246,6 +250,8 @@ class HiFiGANStreamGenerator(_StreamGeneratorBase):
         c.n_up = len(upsample_scales)
         _fill(c.upsample_scales, upsample_scales), _fill(c.upsample_kernel_sizes, upsample_kernel_sizes)
         c.resblock_kernel_size = resblock_kernel_sizes[0]
+        c.n_resblocks = 0 if multi_group else len(resblock_kernel_sizes)
+        _fill(c.resblock_kernel_sizes, resblock_kernel_sizes)
         c.n_dil = len(resblock_dilations[0])
         _fill(c.resblock_dilations, resblock_dilations[0])
         c.groups = groups

@@ -664,8 +664,9 @@ int need_tensor(adec_handle* h, const std::string& key, const HostTensor** out) 
 }
 
 int build_stem(adec_handle* h, Op* op, const std::string& prefix, int cout) {
-    const HostTensor* W;
-    if (need_tensor(h, prefix + ".conv.weight", &W)) return 1;
+    HostTensor Wt;
+    if (get_weight(h, prefix + ".conv", &Wt)) return 1;
+    const HostTensor* W = &Wt;
     if (W->shape[0] != 32 || W->shape[1] != 1 || W->shape[2] != 7 || cout != 32)
         return h->fail("stem conv: only input_channels=1, encode_channels=32, kernel 7 is built");
     op->kind = OP_STEM; op->name = prefix; op->P = 6; op->st_C = 1; op->Cin = 1; op->Cout = 32;
@@ -717,10 +718,10 @@ void chain(Op* op, Wire* w, int out_ld) {
 
 // append a residual unit to `ops`: one fused launch, or (tensor-core path, C > 128) conv + 1x1 launches
 int push_ru(adec_handle* h, std::vector<Op>* ops, Wire* w, const std::string& ru, int dil, int ch) {
-    const HostTensor *W1, *W2;
-    if (need_tensor(h, ru + ".conv1.conv.weight", &W1) || need_tensor(h, ru + ".conv2.weight", &W2)) return 1;
+    HostTensor W1, W2;
+    if (get_weight(h, ru + ".conv1.conv", &W1) || get_weight(h, ru + ".conv2", &W2)) return 1;
     Op op;
-    if (make_ru_op(h, &op, ru, *W1, *W2, dil, ACT_ELU)) return 1;
+    if (make_ru_op(h, &op, ru, W1, W2, dil, ACT_ELU)) return 1;
     load_pad_buffer(h, &op, ru + ".conv1.pad_buffer", ch);
     if (h->use_tc && op.Cout > kTcMaxFuse) {
         Op conv, pw;
@@ -759,21 +760,22 @@ int build_symad(adec_handle* h) {
         const std::string pre = fmt("encoder.conv_blocks.%d", i);
         for (int j = 0; j < 3; ++j)
             if (push_ru(h, &h->enc_ops, &w, pre + fmt(".res_units.%d", j), dils[j], ch)) return 1;
-        const HostTensor* W;
-        if (need_tensor(h, pre + ".conv.conv.weight", &W)) return 1;
+        HostTensor W;
+        if (get_weight(h, pre + ".conv.conv", &W)) return 1;
         const HostTensor* b = find(h, pre + ".conv.conv.bias");
         Op op;
-        if (make_conv_op(h, &op, pre + ".conv", *W, b, c.enc_strides[i], 1, 1, ACT_NONE, 0.f, false)) return 1;
+        if (make_conv_op(h, &op, pre + ".conv", W, b, c.enc_strides[i], 1, 1, ACT_NONE, 0.f, false)) return 1;
         load_pad_buffer(h, &op, pre + ".conv.pad_buffer", ch);
         ch = c.encode_channels * c.enc_ratios[i];
         chain(&op, &w, ch);
         h->enc_ops.push_back(std::move(op));
     }
     {   // projector (projector.py:40,52-54): k=3, no bias; writes z channels-first (B,64,F)
-        const HostTensor* W;
-        if (need_tensor(h, "projector.project.conv.weight", &W)) return 1;
-        Op op;
-        if (make_conv_op(h, &op, "projector.project", *W, find(h, "projector.project.conv.bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
+        HostTensor W;
+        if (get_weight(h, "projector.project.conv", &W)) return 1;
+        Op op;   // symAAD: the encoder's trailing ELU (encoder.py:174-175) is this conv's pre-activation
+        if (make_conv_op(h, &op, "projector.project", W, find(h, "projector.project.conv.bias"), 1, 1, 1,
+                         c.codec_activate ? ACT_ELU : ACT_NONE, 0.f, false)) return 1;
         load_pad_buffer(h, &op, "projector.project.pad_buffer", ch);
         op.in_buf = w.cur; op.ldx = w.cur_ld; op.x_goff = op.Cin;
         op.out_buf = BUF_EXT_OUT; op.out_nct = true; op.ldy = op.Cout; op.y_goff = op.Cout;
@@ -783,22 +785,24 @@ int build_symad(adec_handle* h) {
     // ---- decoder (models/autoencoder/modules/decoder.py:84-148)
     Wire d; d.cur = BUF_EXT_IN; d.cur_ld = c.code_dim;
     {
-        const HostTensor* W;
-        if (need_tensor(h, "decoder.conv1.conv.weight", &W)) return 1;
+        HostTensor W;
+        if (get_weight(h, "decoder.conv1.conv", &W)) return 1;
         Op op;
-        if (make_conv_op(h, &op, "decoder.conv1", *W, find(h, "decoder.conv1.conv.bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
+        if (make_conv_op(h, &op, "decoder.conv1", W, find(h, "decoder.conv1.conv.bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
         load_pad_buffer(h, &op, "decoder.conv1.pad_buffer", c.code_dim);
         chain(&op, &d, op.Cout);
         h->dec_ops.push_back(std::move(op));
     }
     for (int i = 0; i < c.n_dec; ++i) {
-        const std::string pre = fmt("decoder.conv_blocks.%d", i);
+        // symAAD wraps each block as Sequential(ELU, DecoderBlock) -> keys "...conv_blocks.i.1.*" (decoder.py:183-195)
+        const std::string pre = fmt(c.codec_activate ? "decoder.conv_blocks.%d.1" : "decoder.conv_blocks.%d", i);
         const int cin = c.decode_channels * c.dec_ratios[i];
         const int cout = i < c.n_dec - 1 ? c.decode_channels * c.dec_ratios[i + 1] : c.decode_channels;
-        const HostTensor* W;
-        if (need_tensor(h, pre + ".conv.deconv.weight", &W)) return 1;
+        HostTensor W;
+        if (get_weight(h, pre + ".conv.deconv", &W)) return 1;
         Op op;
-        if (make_convtr_op(h, &op, pre + ".conv", *W, find(h, pre + ".conv.deconv.bias"), c.dec_strides[i], ACT_NONE, 0.f)) return 1;
+        if (make_convtr_op(h, &op, pre + ".conv", W, find(h, pre + ".conv.deconv.bias"), c.dec_strides[i],
+                           c.codec_activate ? ACT_ELU : ACT_NONE, 0.f)) return 1;
         if (op.Cout != c.dec_strides[i] * cout) return h->fail(pre + ": stride*Cout must be a multiple of 32");
         load_pad_buffer(h, &op, pre + ".conv.pad_buffer", cin);
         chain(&op, &d, op.Cout);
@@ -809,7 +813,7 @@ int build_symad(adec_handle* h) {
     }
     {
         Op op;
-        if (build_head(h, &op, "decoder.conv2", ACT_NONE, 0.f, false)) return 1;
+        if (build_head(h, &op, "decoder.conv2", c.codec_activate ? ACT_ELU : ACT_NONE, 0.f, c.codec_activate != 0)) return 1;   // decoder.py:209-211
         op.in_buf = d.cur; op.ldx = d.cur_ld; op.out_buf = BUF_EXT_OUT; op.ldy = 1;
         h->dec_ops.push_back(std::move(op));
     }
@@ -843,10 +847,52 @@ int build_symad(adec_handle* h) {
     return 0;
 }
 
+// AD v0 (MultiReceptiveField, multi_fusion.py:23-79): the mean of one residual block per kernel size.  A causal conv with
+// kernel k equals one with kernel K >= k whose first K-k taps are zero, so the three blocks are expressed as ONE grouped
+// conv stack with the largest kernel (zero-padded taps) followed by a 1x1 "conv_out" holding [I/3 I/3 I/3] - exactly
+// the MultiGroupConv1d graph the kernels already run.
+int synthesize_mrf_as_groups(adec_handle* h, int stage, int C, HostTensor W1[], HostTensor B1[], HostTensor W2[], HostTensor B2[],
+                             HostTensor* Wout) {
+    const adec_config& c = h->cfg;
+    const int nb = c.n_resblocks;
+    int K = 0;
+    for (int b = 0; b < nb; ++b) K = std::max(K, c.resblock_kernel_sizes[b]);
+    for (int j = 0; j < c.n_dil; ++j)
+        for (int which = 0; which < 2; ++which) {
+            HostTensor& W = which ? W2[j] : W1[j];
+            HostTensor& Bt = which ? B2[j] : B1[j];
+            W.shape = {nb * C, C, K};
+            W.data.assign((size_t)nb * C * C * K, 0.f);
+            Bt.shape = {nb * C};
+            Bt.data.assign((size_t)nb * C, 0.f);
+            for (int b = 0; b < nb; ++b) {
+                const int kb = c.resblock_kernel_sizes[b];
+                const std::string pre = fmt("blocks.%d.blocks.%d.convs%d.%d", stage, b, which + 1, j);
+                HostTensor w;
+                if (get_weight(h, pre + ".conv", &w)) return 1;
+                if (w.shape.size() != 3 || w.shape[0] != C || w.shape[1] != C || w.shape[2] != kb) return h->fail("bad shape: " + pre);
+                for (int co = 0; co < C; ++co)
+                    for (int ci = 0; ci < C; ++ci)
+                        for (int k = 0; k < kb; ++k)
+                            W.data[((size_t)(b * C + co) * C + ci) * K + (K - kb) + k] = w.data[((size_t)co * C + ci) * kb + k];
+                if (const HostTensor* bb = find(h, pre + ".conv.bias"))
+                    for (int co = 0; co < C; ++co) Bt.data[b * C + co] = bb->data[co];
+                find(h, pre + ".pad_buffer");   // zeros in every released checkpoint; the longer zero-tap history starts at zero too
+            }
+        }
+    Wout->shape = {C, nb * C, 1};
+    Wout->data.assign((size_t)C * nb * C, 0.f);
+    for (int co = 0; co < C; ++co)
+        for (int b = 0; b < nb; ++b) Wout->data[(size_t)co * nb * C + b * C + co] = 1.0f / nb;
+    return 0;
+}
+
 int build_hifigan(adec_handle* h) {
     const adec_config& c = h->cfg;
     if (c.out_channels != 1) return h->fail("HiFi-GAN: only out_channels=1 is built");
-    if (c.groups < 2) return h->fail("HiFi-GAN: only the MultiGroupConv1d (groups>1, one resblock kernel) variant is built");
+    const bool mrf = c.n_resblocks > 0;       // AD v0
+    if (!mrf && c.groups < 2) return h->fail("HiFi-GAN: groups must be > 1 for the MultiGroupConv1d variant");
+    if (mrf && c.groups != 1) return h->fail("HiFi-GAN: MultiReceptiveField needs groups = 1");
     const float slope = c.negative_slope;
     if (c.has_stats) {
         const HostTensor *m, *s;
@@ -883,20 +929,30 @@ int build_hifigan(adec_handle* h) {
             h->dec_ops.push_back(std::move(op));
         }
         // MultiGroupConv1d (multi_fusion.py:82-141): x.repeat folded away (shared_in on the first conv)
-        const int G = c.groups, C3 = G * cout;
+        const int G = mrf ? c.n_resblocks : c.groups, C3 = G * cout;
+        HostTensor mW1[ADEC_MAX_STAGES], mB1[ADEC_MAX_STAGES], mW2[ADEC_MAX_STAGES], mB2[ADEC_MAX_STAGES], mWout;
+        if (mrf && synthesize_mrf_as_groups(h, i, cout, mW1, mB1, mW2, mB2, &mWout)) return 1;
         const int A = w.cur;                 // c (T, cout)
         const int Bb = w.pick();             // xt
         const int Cc = w.pick(Bb);           // x (T, 3C)
         for (int j = 0; j < c.n_dil; ++j) {
             const std::string p1 = fmt("blocks.%d.convs1.%d", i, j), p2 = fmt("blocks.%d.convs2.%d", i, j);
             HostTensor W1, W2;
-            if (get_weight(h, p1 + ".conv", &W1) || get_weight(h, p2 + ".conv", &W2)) return 1;
+            const HostTensor *b1 = nullptr, *b2 = nullptr;
+            if (mrf) {
+                W1 = mW1[j]; W2 = mW2[j]; b1 = &mB1[j]; b2 = &mB2[j];
+            } else {
+                if (get_weight(h, p1 + ".conv", &W1) || get_weight(h, p2 + ".conv", &W2)) return 1;
+                b1 = find(h, p1 + ".conv.bias"); b2 = find(h, p2 + ".conv.bias");
+            }
             Op o1, o2;
-            if (make_conv_op(h, &o1, p1, W1, find(h, p1 + ".conv.bias"), 1, c.resblock_dilations[j], G, ACT_LRELU, slope, j == 0)) return 1;
-            if (make_conv_op(h, &o2, p2, W2, find(h, p2 + ".conv.bias"), 1, 1, G, ACT_LRELU, slope, false)) return 1;
+            if (make_conv_op(h, &o1, p1, W1, b1, 1, c.resblock_dilations[j], G, ACT_LRELU, slope, j == 0)) return 1;
+            if (make_conv_op(h, &o2, p2, W2, b2, 1, 1, G, ACT_LRELU, slope, false)) return 1;
             if (o1.Cout != cout || o1.Cin != cout) return h->fail(p1 + ": channels must be a multiple of 32");
-            load_pad_buffer(h, &o1, p1 + ".pad_buffer", cout);
-            load_pad_buffer(h, &o2, p2 + ".pad_buffer", cout);
+            if (!mrf) {
+                load_pad_buffer(h, &o1, p1 + ".pad_buffer", cout);
+                load_pad_buffer(h, &o2, p2 + ".pad_buffer", cout);
+            }
             o1.in_buf = j == 0 ? A : Cc; o1.ldx = j == 0 ? cout : C3; o1.x_goff = j == 0 ? 0 : cout;
             o1.out_buf = Bb; o1.ldy = C3; o1.y_goff = cout;
             o2.in_buf = Bb; o2.ldx = C3; o2.x_goff = cout;
@@ -908,7 +964,8 @@ int build_hifigan(adec_handle* h) {
         {
             HostTensor W;
             const std::string po = fmt("blocks.%d.conv_out", i);
-            if (get_weight(h, po, &W)) return 1;
+            if (mrf) W = mWout;
+            else if (get_weight(h, po, &W)) return 1;
             Op op;
             if (make_conv_op(h, &op, po, W, find(h, po + ".bias"), 1, 1, 1, ACT_NONE, 0.f, false)) return 1;
             op.in_buf = Cc; op.ldx = C3; op.x_goff = op.Cin;

@@ -39,6 +39,12 @@ HIFIGAN_V1_PARAMS = dict(
     stats="stats/synthetic.npy",
 )
 
+SYMAD_C16_PARAMS = dict(SYMAD_PARAMS, codebook_num=16, enc_strides=[2, 4, 5, 8], dec_strides=[8, 5, 4, 2])
+SYMAAD_PARAMS = dict(SYMAD_PARAMS, codec="activate_audiodec", use_weight_norm=True)
+HIFIGAN_V2_PARAMS = dict(HIFIGAN_V1_PARAMS, resblock_kernel_sizes=[3])
+HIFIGAN_V0_PARAMS = dict(HIFIGAN_V1_PARAMS, groups=1, resblock_kernel_sizes=[3, 7, 11],
+                         resblock_dilations=[[1, 3, 5], [1, 3, 5], [1, 3, 5]])
+
 # model name -> (sample_rate, encoder tag, encoder steps, decoder kind, decoder tag, decoder steps)
 # mirrors the table in utils/audiodec.py:109-179 (only the entries this repo implements).
 MODEL_TABLE = {
@@ -46,7 +52,15 @@ MODEL_TABLE = {
     "vctk_v1": (48000, "symAD_vctk_48000_hop300", 200000, "vocoder", "AudioDec_v1_symAD_vctk_48000_hop300_clean", 500000),
     "libritts_sym": (24000, "symAD_libritts_24000_hop300", 500000, "autoencoder", "symAD_libritts_24000_hop300", 1000000),
     "libritts_v1": (24000, "symAD_libritts_24000_hop300", 500000, "vocoder", "AudioDec_v1_symAD_libritts_24000_hop300_clean", 500000),
+    "vctk_v0": (48000, "symAD_vctk_48000_hop300", 200000, "vocoder", "AudioDec_v0_symAD_vctk_48000_hop300_clean", 500000),
+    "vctk_v2": (48000, "symAD_vctk_48000_hop300", 200000, "vocoder", "AudioDec_v2_symAD_vctk_48000_hop300_clean", 500000),
+    "vctk_activate_sym": (48000, "symAAD_vctk_48000_hop300", 200000, "autoencoder", "symAAD_vctk_48000_hop300", 700000),
+    "vctk_c16h320_sym": (48000, "symAD_c16_vctk_48000_hop320", 500000, "autoencoder", "symAD_c16_vctk_48000_hop320", 1000000),
 }
+# which generator_params each checkpoint directory uses
+ENCODER_PARAMS = {"symAAD_vctk_48000_hop300": SYMAAD_PARAMS, "symAD_c16_vctk_48000_hop320": SYMAD_C16_PARAMS}
+VOCODER_PARAMS = {"AudioDec_v0_symAD_vctk_48000_hop300_clean": HIFIGAN_V0_PARAMS,
+                  "AudioDec_v2_symAD_vctk_48000_hop300_clean": HIFIGAN_V2_PARAMS}
 
 
 def _randn(gen, *shape, std=1.0):
@@ -66,15 +80,26 @@ def symad_state_dict(params=None, seed=0, codebook_scale=None):
     ec, dc = p["encode_channels"], p["decode_channels"]
     k = 7
 
+    wn = bool(p.get("use_weight_norm", False))          # symAAD: every conv is weight-normed (AudioDec.py:152-162)
+    act = p.get("codec", "audiodec") == "activate_audiodec"
+
+    def put_weight(key, w):
+        """plain `weight`, or an equivalent (weight_g, weight_v) pair: w = g * v/||v|| over dims != 0"""
+        if not wn:
+            sd[key + ".weight"] = w
+        else:
+            sd[key + ".weight_g"] = w.flatten(1).norm(dim=1).reshape(-1, 1, 1)
+            sd[key + ".weight_v"] = w * (0.5 + torch.rand(w.shape[0], 1, 1, generator=g))   # any per-row rescale of v
+
     def conv(prefix, cout, cin, ks, bias, gain=1.0, dil=1, sub="conv"):
         sd[f"{prefix}.pad_buffer"] = torch.zeros(1, cin, (ks - 1) * dil)
-        sd[f"{prefix}.{sub}.weight"] = _randn(g, cout, cin, ks, std=gain / (cin * ks) ** 0.5)
+        put_weight(f"{prefix}.{sub}", _randn(g, cout, cin, ks, std=gain / (cin * ks) ** 0.5))
         if bias:
             sd[f"{prefix}.{sub}.bias"] = _randn(g, cout, std=0.1)
 
     def res_unit(prefix, c, dil):
         conv(f"{prefix}.conv1", c, c, k, False, gain=1.2, dil=dil)
-        sd[f"{prefix}.conv2.weight"] = _randn(g, c, c, 1, std=0.6 / c ** 0.5)
+        put_weight(f"{prefix}.conv2", _randn(g, c, c, 1, std=0.6 / c ** 0.5))
 
     # encoder (models/autoencoder/modules/encoder.py:84-142)
     conv("encoder.conv", ec, p["input_channels"], k, False, gain=3.0)
@@ -91,9 +116,9 @@ def symad_state_dict(params=None, seed=0, codebook_scale=None):
     for i, s in enumerate(p["dec_strides"]):
         cin = dc * p["dec_ratios"][i]
         cout = dc * p["dec_ratios"][i + 1] if i < len(p["dec_strides"]) - 1 else dc
-        pre = f"decoder.conv_blocks.{i}"
+        pre = f"decoder.conv_blocks.{i}.1" if act else f"decoder.conv_blocks.{i}"     # decoder.py:183-195: Sequential(act, block)
         sd[f"{pre}.conv.pad_buffer"] = torch.zeros(1, cin, 1)
-        sd[f"{pre}.conv.deconv.weight"] = _randn(g, cin, cout, 2 * s, std=0.8 / (2 * cin) ** 0.5)
+        put_weight(f"{pre}.conv.deconv", _randn(g, cin, cout, 2 * s, std=0.8 / (2 * cin) ** 0.5))
         if p["bias"]:
             sd[f"{pre}.conv.deconv.bias"] = _randn(g, cout, std=0.1)
         for j, d in enumerate((1, 3, 9)):
@@ -144,6 +169,14 @@ def hifigan_state_dict(params=None, seed=1):
         # weight norm over dims (1,2) of (Cin,Cout,K): one g per INPUT channel
         sd[f"{pre}.deconv.weight_g"] = 1.4 * (cout * 2 * s) ** 0.5 / (2 * cin) ** 0.5 * (0.75 + 0.5 * torch.rand(cin, 1, 1, generator=g))
         sd[f"{pre}.deconv.weight_v"] = _randn(g, cin, cout, 2 * s, std=1.0)
+        if grp == 1 and len(p["resblock_kernel_sizes"]) > 1:
+            # AD v0: MultiReceptiveField = mean of one HiFiGANResidualBlock per kernel size (multi_fusion.py:23-79)
+            for b, (rkb, dilb) in enumerate(zip(p["resblock_kernel_sizes"], p["resblock_dilations"])):
+                for j, d in enumerate(dilb):
+                    wn_conv(f"blocks.{i}.blocks.{b}.convs1.{j}", cout, cout, rkb, p["bias"], gain=0.9, dil=d)
+                for j, d in enumerate(dilb):
+                    wn_conv(f"blocks.{i}.blocks.{b}.convs2.{j}", cout, cout, rkb, p["bias"], gain=0.5, dil=1)
+            continue
         c3 = cout * grp
         for j, d in enumerate(dils):
             wn_conv(f"blocks.{i}.convs1.{j}", c3, cout, rk, p["bias"], gain=0.9, dil=d, cin_total=c3)
@@ -185,14 +218,16 @@ def make_model_zoo(root, model="vctk_sym", seed=0):
     Returns (sample_rate, encoder_checkpoint, decoder_checkpoint) as absolute paths."""
     import numpy as np
     sr, etag, esteps, dkind, dtag, dsteps = MODEL_TABLE[model]
-    enc_sd = symad_state_dict(seed=seed)
-    enc = write_checkpoint(root, "autoencoder", etag, esteps, "symAudioDec", dict(SYMAD_PARAMS), enc_sd, sr)
+    eparams = dict(ENCODER_PARAMS.get(etag, SYMAD_PARAMS))
+    enc_sd = symad_state_dict(eparams, seed=seed)
+    enc = write_checkpoint(root, "autoencoder", etag, esteps, "symAudioDec", eparams, enc_sd, sr)
     if dkind == "autoencoder":
-        dec = write_checkpoint(root, "autoencoder", dtag, dsteps, "symAudioDec", dict(SYMAD_PARAMS), enc_sd, sr)
+        dec = write_checkpoint(root, "autoencoder", dtag, dsteps, "symAudioDec", eparams, enc_sd, sr)
     else:
-        dec_sd = hifigan_state_dict(seed=seed + 1)
+        vparams = dict(VOCODER_PARAMS.get(dtag, HIFIGAN_V1_PARAMS))
+        dec_sd = hifigan_state_dict(vparams, seed=seed + 1)
         os.makedirs(os.path.join(root, "stats"), exist_ok=True)
         np.save(os.path.join(root, "stats", "synthetic.npy"),
                 np.stack([dec_sd["mean"].numpy(), dec_sd["scale"].numpy()]).astype("float32"))
-        dec = write_checkpoint(root, "vocoder", dtag, dsteps, "HiFiGAN", dict(HIFIGAN_V1_PARAMS), dec_sd, sr)
+        dec = write_checkpoint(root, "vocoder", dtag, dsteps, "HiFiGAN", vparams, dec_sd, sr)
     return sr, enc, dec

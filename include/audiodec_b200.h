@@ -58,6 +58,9 @@ typedef struct adec_config {
     float negative_slope;
     int use_weight_norm;
     int has_stats;
+    /* appended in round 1 (variants of SURVEY.md 8(f) rank 1) */
+    int codec_activate;                                    /* symAAD: codec='activate_audiodec' (encoder.py:145-175, decoder.py:151-214) */
+    int n_resblocks;  int resblock_kernel_sizes[ADEC_MAX_STAGES];   /* AD v0: MultiReceptiveField, one residual block per kernel size */
 } adec_config;
 
 /* -- lifetime ---------------------------------------------------------------- */

@@ -104,6 +104,13 @@ class SymADOracle:
     def __init__(self, params, state_dict):
         self.p = dict(params)
         self.sd = {k: v.detach().clone().float() for k, v in state_dict.items()}
+        # use_weight_norm (symAAD, AudioDec.py:152-162): weight = g * v/||v||, recomputed per call in the reference
+        for k in list(self.sd):
+            if k.endswith("weight_g"):
+                base = k[:-len("weight_g")]
+                self.sd[base + "weight"] = fold_weight_norm(self.sd[k], self.sd[base + "weight_v"])
+        # codec='activate_audiodec' (ActivateEncoder/ActivateDecoder, encoder.py:145-175, decoder.py:151-214)
+        self.activate = self.p.get("codec", "audiodec") == "activate_audiodec"
         self.state = OrderedDict()
         self.reset_buffer()
         self.embeds = [self.sd[f"quantizer.codebook.layers.{i}.embed"] for i in range(self.p["codebook_num"])]
@@ -158,6 +165,8 @@ class SymADOracle:
             for j, d in enumerate((1, 3, 9)):
                 h = self._res_unit(f"encoder.conv_blocks.{i}.res_units.{j}", h, d)
             h = self._conv(f"encoder.conv_blocks.{i}.conv", h, stride=s)
+        if self.activate:
+            h = F.elu(h)                                 # encoder.py:174-175
         return self._conv("projector.project", h)        # projector.py:52-54
 
     def quantize(self, z, return_margins=False):         # AudioDec.py:237-239 -> quantizer.py:42-44
@@ -175,12 +184,16 @@ class SymADOracle:
         self._ensure_batch(zq.shape[0])
         h = self._conv("decoder.conv1", zq.transpose(2, 1))
         for i, s in enumerate(self.p["dec_strides"]):
-            n = f"decoder.conv_blocks.{i}"
+            n = f"decoder.conv_blocks.{i}.1" if self.activate else f"decoder.conv_blocks.{i}"
+            if self.activate:
+                h = F.elu(h)                             # decoder.py:207 conv_blocks[i][0]
             h, self.state[f"{n}.conv"] = causal_convtr1d_infer(
                 h, self.sd[f"{n}.conv.deconv.weight"], self.sd.get(f"{n}.conv.deconv.bias"),
                 self.state[f"{n}.conv"], s)
             for j, d in enumerate((1, 3, 9)):
                 h = self._res_unit(f"{n}.res_units.{j}", h, d)
+        if self.activate:
+            return torch.tanh(self._conv("decoder.conv2", F.elu(h)))      # decoder.py:209-211
         return self._conv("decoder.conv2", h)
 
 
@@ -235,6 +248,19 @@ class HiFiGANOracle:
             c, self.state[n] = causal_convtr1d_infer(
                 F.leaky_relu(c, self.slope), self.w[f"{n}.deconv.weight"], self.w.get(f"{n}.deconv.bias"),
                 self.state[n], s)
+            if grp == 1 and len(self.p["resblock_kernel_sizes"]) > 1:
+                # AD v0: MultiReceptiveField.inference (multi_fusion.py:73-79) over HiFiGANResidualBlock.inference
+                # (residual_block.py:100-105)
+                cs = 0.0
+                for bk, dils in enumerate(self.p["resblock_dilations"]):
+                    x = c
+                    for j, d in enumerate(dils):
+                        xt = self._conv(f"blocks.{i}.blocks.{bk}.convs1.{j}", F.leaky_relu(x, self.slope), d)
+                        xt = self._conv(f"blocks.{i}.blocks.{bk}.convs2.{j}", F.leaky_relu(xt, self.slope), 1)
+                        x = xt + x
+                    cs = cs + x
+                c = cs / len(self.p["resblock_dilations"])
+                continue
             x = c.repeat(1, grp, 1)                      # multi_fusion.py:134
             for j, d in enumerate(self.p["resblock_dilations"][0]):   # :135-139
                 xt = self._conv(f"blocks.{i}.convs1.{j}", F.leaky_relu(x, self.slope), d, grp)

@@ -155,6 +155,22 @@ def main():
     np.savez_compressed(os.path.join(HERE, "v1_stream.npz"), x=xv.numpy(), y=torch.cat(ys, -1).numpy(), chunk=1500,
                         enc_digest=enc_digest, dec_digest=dec_digest, **meta)
 
+    # ---- 5b. the other released variants (assign_model table, utils/audiodec.py:109-179): one short clip each
+    for model, name in (("vctk_v2", "v2_oneshot"), ("vctk_v0", "v0_oneshot"), ("vctk_activate_sym", "aad_oneshot"),
+                        ("vctk_c16h320_sym", "c16_oneshot")):
+        torch.manual_seed(21)
+        xm = 0.1 * torch.randn(1, 1, 6400)
+        a = load_codec(scratch, model)
+        zm, idxm, zqm, ym = run_path(a, xm)
+        a = load_codec(scratch, model)
+        ys, idxs = [], []
+        for c in range(2):          # and as two 3200-sample chunks (3200 = 10 hops of 320 = not a multiple of 300: ragged for hop 300)
+            _, ic, _, yc = run_path(a, xm[:, :, c * 3200:(c + 1) * 3200])
+            ys.append(yc), idxs.append(ic)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), x=xm.numpy(), z=zm.numpy(), idx=idxm.numpy(), zq=zqm.numpy(),
+                            y=ym.numpy(), y_chunks=torch.cat(ys, -1).numpy(), idx_chunks=torch.cat(idxs, -1).numpy(), **meta)
+        print(name, "idx", tuple(idxm.shape), "y", tuple(ym.shape), "absmax", ym.abs().max().item())
+
     # ---- 6. layer-level known-answer cases straight from the reference layer classes
     from layers.conv_layer import CausalConv1d, CausalConvTranspose1d
     from layers.vq_module import ResidualVQ

@@ -66,6 +66,10 @@ def test_unsupported_variants_raise_like_the_reference():
     from audiodec_b200.codec import HiFiGANStreamGenerator, SymADStreamGenerator
     with pytest.raises(NotImplementedError):
         SymADStreamGenerator(codec="unknown")
+    SymADStreamGenerator(codec="activate_audiodec", use_weight_norm=True)      # symAAD is built
+    HiFiGANStreamGenerator(in_channels=64, groups=1)                           # AD v0 (MultiReceptiveField) is built
+    with pytest.raises(NotImplementedError):
+        HiFiGANStreamGenerator(groups=1, resblock_dilations=[(1, 3, 5), (1, 3), (1, 3, 5)])
     with pytest.raises(AssertionError):
         SymADStreamGenerator(mode="noncausal")             # models/utils.py:13-15
     with pytest.raises(AssertionError):

@@ -132,3 +132,31 @@ def test_layer_rvq(golden_dir):
     np.testing.assert_allclose(zq.numpy(), c["zq"], atol=1e-6)
     cb = torch.stack([e.T for e in embeds]).reshape(-1, 16)
     np.testing.assert_allclose(O.rvq_lookup(idx.squeeze(1), cb).numpy(), c["lookup"], atol=1e-6)
+
+
+VARIANTS = {   # golden file -> (encoder params, vocoder params or None)
+    "v2_oneshot.npz": ("SYMAD_PARAMS", "HIFIGAN_V2_PARAMS"),
+    "v0_oneshot.npz": ("SYMAD_PARAMS", "HIFIGAN_V0_PARAMS"),
+    "aad_oneshot.npz": ("SYMAAD_PARAMS", None),
+    "c16_oneshot.npz": ("SYMAD_C16_PARAMS", None),
+}
+
+
+@pytest.mark.parametrize("fname", sorted(VARIANTS))
+def test_released_variants(golden_dir, fname):
+    """HiFi-GAN v2 (k=3) / v0 (MultiReceptiveField), symAAD (weight-normed, ELU/tanh), 16-codebook hop-320 symAD:
+    one-shot and two-chunk streaming vs the unmodified reference."""
+    g = _load(golden_dir, fname)
+    ep, vp = (getattr(S, n) if n else None for n in VARIANTS[fname])
+    esd = S.symad_state_dict(ep, seed=0)
+    vsd = S.hifigan_state_dict(vp, seed=1) if vp else None
+    x = torch.from_numpy(g["x"])
+    c = O.CodecOracle(ep, esd, vp, vsd)
+    z, idx, zq, y = c.run(x)
+    assert tuple(idx.shape) == tuple(g["idx"].shape)
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=TOL)
+    c = O.CodecOracle(ep, esd, vp, vsd)
+    outs = [c.run(x[:, :, i:i + 3200]) for i in (0, 3200)]
+    np.testing.assert_array_equal(torch.cat([o[1] for o in outs], -1).numpy(), g["idx_chunks"])
+    np.testing.assert_allclose(torch.cat([o[3] for o in outs], -1).numpy(), g["y_chunks"], atol=TOL)

@@ -186,3 +186,48 @@ def test_codec_host_path_matches_device_path(golden_dir, symad_sd):
     assert tuple(idx_h.shape) == (8, 3, 20) and not idx_h.is_cuda and not y_h.is_cuda
     np.testing.assert_array_equal(idx_h.numpy(), g["idx"])
     np.testing.assert_allclose(y_h.numpy(), g["y"], atol=WAVE_TOL)
+
+
+VARIANTS = {   # golden file -> (encoder params, vocoder params or None)
+    "v2_oneshot.npz": ("SYMAD_PARAMS", "HIFIGAN_V2_PARAMS"),
+    "v0_oneshot.npz": ("SYMAD_PARAMS", "HIFIGAN_V0_PARAMS"),
+    "aad_oneshot.npz": ("SYMAAD_PARAMS", None),
+    "c16_oneshot.npz": ("SYMAD_C16_PARAMS", None),
+}
+
+
+def _variant_codec(ep, esd, vp, vsd):
+    from audiodec_b200.codec import HiFiGANStreamGenerator, SymADStreamGenerator
+    dev = torch.device("cuda:0")
+    objs = []
+    for _ in range(3):
+        g = SymADStreamGenerator(**ep)
+        g.load_state_dict(esd)
+        objs.append(g)
+    tx, rx, dec = objs
+    if vp is not None:
+        dec = HiFiGANStreamGenerator(**vp)
+        dec.load_state_dict(vsd)
+    tx, rx, dec = tx.eval().to(dev), rx.eval().to(dev), dec.eval().to(dev)
+    tx.initial_encoder(8192, dev)
+    dec.initial_decoder(rx.initial_encoder(8192, dev))
+    return tx, rx, dec
+
+
+@pytest.mark.parametrize("fname", sorted(VARIANTS))
+def test_released_variants_golden(golden_dir, fname):
+    """The rest of the assign_model table (utils/audiodec.py:109-179): HiFi-GAN v2 / v0, symAAD, 16-codebook hop-320."""
+    g = np.load(os.path.join(golden_dir, fname))
+    ep, vp = (getattr(S, n) if n else None for n in VARIANTS[fname])
+    esd = S.symad_state_dict(ep, seed=0)
+    vsd = S.hifigan_state_dict(vp, seed=1) if vp else None
+    x = torch.from_numpy(g["x"])
+    tx, rx, dec = _variant_codec(ep, esd, vp, vsd)
+    z, idx, zq, y = _run(tx, rx, dec, x)
+    assert tuple(idx.shape) == tuple(g["idx"].shape) and tuple(y.shape) == tuple(g["y"].shape)
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=WAVE_TOL)
+    tx, rx, dec = _variant_codec(ep, esd, vp, vsd)
+    outs = [_run(tx, rx, dec, x[:, :, i:i + 3200]) for i in (0, 3200)]
+    np.testing.assert_array_equal(torch.cat([o[1] for o in outs], -1).numpy(), g["idx_chunks"])
+    np.testing.assert_allclose(torch.cat([o[3] for o in outs], -1).numpy(), g["y_chunks"], atol=WAVE_TOL)

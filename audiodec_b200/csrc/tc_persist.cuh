@@ -38,6 +38,8 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
     constexpr int PPG = HALF ? 1 : NCOL / CP;            // 32-column pieces (or half pieces) owned by one drain group
     constexpr int UC = HALF ? NCOL : CP;                 // columns per owned unit
     constexpr int MB = TcpCfg<NT>::MB;
+    constexpr bool PIPE = FUSE && NT == 32;              // conv of tile i+1 issued before the 1x1 conv of tile i (needs 2*NCOL drain registers;
+                                                         // measured: -19 % at NT=32, +3 % (register spills) at NT=64)
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     constexpr uint32_t TMEM_COLS = NPB * NT;
 
@@ -91,15 +93,26 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
         // ------------------------------------------------ weight producer
         if (lane == 0) {
             int c = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int y = (tile / n_xtiles) % n_ytiles;
-                const float* w1 = a.w + (long long)y * a.w_tile_floats;
-                for (int k = 0; k < n_g1 + n_g2; ++k, ++c) {
+            auto stream = [&](const float* base, int n) {
+                for (int k = 0; k < n; ++k, ++c) {
                     const int s = c % S, it = c / S;
                     if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1, 100);
-                    const float* src = k < n_g1 ? w1 + (long long)k * BST : a.w2 + (long long)(k - n_g1) * BST;
                     mbar_arrive_expect_tx(&b_full[s], BST * 4);
-                    bulk_g2s(bst + s * BST, src, BST * 4, &b_full[s]);
+                    bulk_g2s(bst + s * BST, base + (long long)k * BST, BST * 4, &b_full[s]);
+                }
+            };
+            auto w1_of = [&](int tile) { return a.w + (long long)((tile / n_xtiles) % n_ytiles) * a.w_tile_floats; };
+            if (PIPE) {
+                // same order as the MMA warps: G1(t0), then per tile { G1(next), G2(this) }
+                if ((int)blockIdx.x < n_tiles) stream(w1_of(blockIdx.x), n_g1);
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    if (tile + (int)gridDim.x < n_tiles) stream(w1_of(tile + gridDim.x), n_g1);
+                    stream(a.w2, n_g2);
+                }
+            } else {
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    stream(w1_of(tile), n_g1);
+                    if (FUSE) stream(a.w2, n_g2);
                 }
             }
         }
@@ -138,9 +151,8 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
             }
             __syncwarp();
         };
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            ++ti; c_tile0 = c;
-            const uint32_t lbo1 = (uint32_t)wrp * 16u;
+        const uint32_t lbo1 = (uint32_t)wrp * 16u, lbo2 = (uint32_t)MIDP * 16u;
+        auto gemm1 = [&]() {        // one tile's conv over its window pieces
             for (int p = 0; p < a.n_pieces; ++p, ++wp) {
                 const int buf = wp & 1;
                 mbar_wait(&w_full[buf], (wp >> 1) & 1, 200);
@@ -151,16 +163,30 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 if (elect_one()) umma_commit(&w_empty[buf]);
                 __syncwarp();
             }
-            if (FUSE) {
-                const uint32_t lbo2 = (uint32_t)MIDP * 16u;
-                for (int p = 0; p < NT / CP; ++p, ++mp, ++c) {
-                    const int mb = mp % MB;
-                    mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
-                    const uint32_t m_hi = mbuf_u + (uint32_t)mb * (2u * CP * MIDP * 4u);
-                    if ((c & 1) == mw) issue_group(m_hi, m_hi + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
-                    if (elect_one()) umma_commit(&m_empty[mb]);
-                    __syncwarp();
-                }
+        };
+        auto gemm2 = [&]() {        // the fused 1x1 conv over the intermediate pieces
+            for (int p = 0; p < NT / CP; ++p, ++mp, ++c) {
+                const int mb = mp % MB;
+                mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
+                const uint32_t m_hi = mbuf_u + (uint32_t)mb * (2u * CP * MIDP * 4u);
+                if ((c & 1) == mw) issue_group(m_hi, m_hi + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
+                if (elect_one()) umma_commit(&m_empty[mb]);
+                __syncwarp();
+            }
+        };
+        if (PIPE) {
+            // software-pipelined order: the conv of tile i+1 is issued BEFORE the 1x1 conv of tile i, so the tensor pipe
+            // works on it while the drain warps turn tile i's accumulators into the 1x1 conv's operand
+            if ((int)blockIdx.x < n_tiles) { ++ti; c_tile0 = c; gemm1(); }
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (tile + (int)gridDim.x < n_tiles) { ++ti; c_tile0 = c; gemm1(); }
+                gemm2();
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                ++ti; c_tile0 = c;
+                gemm1();
+                if (FUSE) gemm2();
             }
         }
     } else if (warp >= 4 && warp < DRAIN0) {
@@ -290,7 +316,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
         float4 rpre[PREFETCH_RES ? PPG : 1][UC / 4];
         int c = 0, mq = 0, ti = -1, c_tile0 = 0;
         int m_seen[2] = {0, 0};
-        auto drain = [&](int ngroups) {
+        auto drain = [&](float (&acc)[NCOL], int ngroups) {
             for (int gi = 0; gi < ngroups; ++gi, ++c) {
                 const int pb = c % NPB;
                 mbar_wait(&p_full[pb], (c / NPB) & 1, 600);
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                     tmem_ld16(tmem + lane_base + (uint32_t)pb * NT + (uint32_t)dg * UC, r0);
                     tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) racc[i] = __fadd_rn(racc[i], __uint_as_float(r0[i]));
+                    for (int i = 0; i < 16; ++i) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
                 } else {
 #pragma unroll
                     for (int pl = 0; pl < PPG; ++pl) {
@@ -312,8 +338,8 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
-                            racc[pl * UC + i] = __fadd_rn(racc[pl * UC + i], __uint_as_float(r0[i]));
-                            racc[pl * UC + 16 + i] = __fadd_rn(racc[pl * UC + 16 + i], __uint_as_float(r1[i]));
+                            acc[pl * UC + i] = __fadd_rn(acc[pl * UC + i], __uint_as_float(r0[i]));
+                            acc[pl * UC + 16 + i] = __fadd_rn(acc[pl * UC + 16 + i], __uint_as_float(r1[i]));
                         }
                     }
                 }
@@ -322,6 +348,12 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 if (tid == DRAIN0 * 32) TLP(5, c - c_tile0);
             }
         };
+        float oacc[PIPE ? NCOL : 1];                         // PIPE: 1x1-conv sums of tile i while racc already holds tile i+1
+        if (PIPE && (int)blockIdx.x < n_tiles) {
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+            drain(racc, n_g1);                                // conv of the first tile
+        }
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             ++ti; c_tile0 = c;
 #ifdef ADEC_TIMELINE
@@ -329,9 +361,11 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
 #endif
             const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
             const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+            if (!PIPE) {
 #pragma unroll
-            for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
-            drain(n_g1);
+                for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+                drain(racc, n_g1);
+            }
             if (FUSE) {
                 // activation first (registers only), so that it overlaps the wait for a free intermediate buffer
 #pragma unroll
@@ -368,7 +402,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
 #pragma unroll
                 for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
                 if (PREFETCH_RES && a.res && j0 + row < a.Tout) {
-                    // the skip tensor's rows are known now: fetch them while the 1x1 conv's MMAs run
+                    // the skip tensor's rows are known now: fetch them while the MMAs run
 #pragma unroll
                     for (int pl = 0; pl < PPG; ++pl) {
                         const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
@@ -377,15 +411,24 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                         for (int i = 0; i < UC / 4; ++i) rpre[pl][i] = __ldg(reinterpret_cast<const float4*>(rp) + i);
                     }
                 }
-                drain(n_g2);
+                if (PIPE) {
+                    // partials arrive in MMA issue order: the NEXT tile's conv first (into racc), then this tile's 1x1 conv
+                    if (tile + (int)gridDim.x < n_tiles) drain(racc, n_g1);
+#pragma unroll
+                    for (int i = 0; i < (PIPE ? NCOL : 1); ++i) oacc[i] = 0.f;
+                    drain(reinterpret_cast<float (&)[NCOL]>(oacc), n_g2);
+                } else {
+                    drain(racc, n_g2);
+                }
             }
+            float* const outv = PIPE ? oacc : racc;
             // ---- epilogue: row `row` of the tile, this group's PPG pieces of 32 channels
             const int t = j0 + row;
             if (t < a.Tout) {
 #pragma unroll
                 for (int pl = 0; pl < PPG; ++pl) {
                     const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
-                    float* v = racc + pl * UC;
+                    float* v = outv + pl * UC;
                     if (a.bias) {
 #pragma unroll
                         for (int i = 0; i < UC / 4; ++i) {

@@ -430,12 +430,16 @@ int pick_piece_width(const Op& op) {
 
 // choose the kernel instantiation, pack + upload weights, allocate state
 int finalize_op_tc(adec_handle* h, Op* op) {
-    const int NT = op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
+    int NT = op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
+    // 96 outputs (transposed conv 64 -> 3*32): one zero-padded 128-wide tile beats three 32-wide tiles that each rebuild the
+    // same activation window and are smem-operand bound (persistent kernel only: its epilogue masks per 32-column piece)
+    const bool pad_tile = !op->fuse && NT == 32 && op->Cout > 64 && op->Cout < 128 && (h->persist_mask & 128);
+    if (pad_tile) NT = 128;
     op->tc = find_tc_kernel(NT, op->fuse, op->pre_act);
     if (!op->tc || (op->fuse && (NT != op->Cout || op->mid_act != op->pre_act))) return h->fail(op->name + ": no tensor-core kernel");
     const int KS = op->tc->KS, CP = TC_CP;
     op->n_pieces = op->Cin_eff / CP;
-    op->n_co_tiles = op->Cout / NT;
+    op->n_co_tiles = pad_tile ? 1 : op->Cout / NT;
     op->w_tile_floats = (long long)op->Ktaps * op->Cin_eff * NT * 2;
     // stage c = ((piece*Ktaps + tap)*(CP/KS) + ks): [hi: (KS/4)][NT][4] | [lo: same]   (UMMA K-major, no swizzle)
     auto pack = [&](const float* weff, int G, int ntiles, int pieces, int taps, int cin_eff, int cout, std::vector<float>* out) {
@@ -452,7 +456,7 @@ int finalize_op_tc(adec_handle* h, Op* op) {
                                 for (int n = 0; n < NT; ++n)
                                     for (int e = 0; e < 4; ++e) {
                                         const int k = pc * CP + ks * KS + c4 * 4 + e;
-                                        const float w = weff[(((size_t)g * taps + tap) * cin_eff + k) * cout + nt * NT + n];
+                                        const float w = nt * NT + n < cout ? weff[(((size_t)g * taps + tap) * cin_eff + k) * cout + nt * NT + n] : 0.f;
                                         const float wh = tf32_round_host(w);
                                         hi[((size_t)c4 * NT + n) * 4 + e] = wh;
                                         lo[((size_t)c4 * NT + n) * 4 + e] = tf32_round_host(w - wh);

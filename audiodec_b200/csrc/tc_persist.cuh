@@ -428,6 +428,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
 #pragma unroll
                 for (int pl = 0; pl < PPG; ++pl) {
                     const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
+                    if (co_l >= a.Cout_g) continue;            // zero-padded part of a channel tile (e.g. 96 outputs in a 128-wide tile)
                     float* v = outv + pl * UC;
                     if (a.bias) {
 #pragma unroll

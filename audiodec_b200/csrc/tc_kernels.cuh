@@ -89,6 +89,29 @@ constexpr int TC_TT = 128;        // output rows per CTA (UMMA M)
 constexpr int TC_CP = 32;         // channels per activation piece == K of one weight stage
 constexpr int TC_MIDP = 129;      // row pitch (rows) of the 1x1 conv's activated operand (odd)
 
+// Two MMA warps take alternate groups c = 0,1,2,... of one weight ring with S stages.  When S is odd, consecutive phases of a
+// stage's b_full barrier belong to DIFFERENT warps, and an mbarrier parity wait only tells "phase k complete" from "phase k
+// pending" for a waiter that knows phase k-1 has completed (otherwise a pending phase k-1 reads as a completed phase k: the warp
+// would issue MMAs on a stage whose TMA load has not landed and release it early; seen as rare hangs when two weight loads
+// landed out of order).  So each warp publishes the last group whose weights it has seen land, and before waiting for group c a
+// warp makes sure the other one has seen group c - S, the previous phase of the same stage.  With S even a stage always belongs
+// to the same warp and nothing is needed.
+template <int S> __device__ __forceinline__ void mma_wait_turn(volatile int* prog, int mw, int c) {
+    if ((S & 1) && c >= S) {
+        long long t0 = 0;
+        unsigned spins = 0;
+        while (prog[mw ^ 1] < c - S) {
+            if ((++spins & 0xfffu) == 0) {
+                if (t0 == 0) t0 = clock64();
+                else if (clock64() - t0 > 4000000000ll) { printf("adec: MMA warp order wait timed out: group %d\n", c); __trap(); }
+            }
+        }
+    }
+}
+template <int S> __device__ __forceinline__ void mma_publish(volatile int* prog, int mw, int c, int lane) {
+    if (S & 1) { if (lane == 0) prog[mw] = c; }
+}
+
 template <int NT>
 struct TcCfg {
     static constexpr int STAGES = NT == 64 ? 4 : 3;
@@ -127,6 +150,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
     uint64_t* p_full = a_empty + 2;                                // [2]  TMEM partial complete
     uint64_t* p_empty = p_full + 2;                                // [2]  TMEM partial drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + 2);
+    volatile int* mma_prog = reinterpret_cast<volatile int*>(smem_raw + 240);   // [2] see mma_wait_turn
     float* bst = reinterpret_cast<float*>(smem_raw + 256);
     const int wrows = TT + (a.Ktaps - 1) * a.dil;
     const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
@@ -151,6 +175,7 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
             mbar_init(&a_full[i], NPROD); mbar_init(&a_empty[i], 2);   // both MMA warps release a piece
             mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG);
         }
+        mma_prog[0] = -1; mma_prog[1] = -1;
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -208,7 +233,9 @@ __global__ void __launch_bounds__(TcCfg<NT>::THREADS, TcCfg<NT>::MIN_CTAS) tc_co
                 for (int tap = 0; tap < taps; ++tap, ++c) {
                     if ((c & 1) != mw) continue;
                     const int s = c % S, pb = c & 1;
+                    mma_wait_turn<S>(mma_prog, mw, c);
                     mbar_wait(&b_full[s], (c / S) & 1, 300 + c);
+                    mma_publish<S>(mma_prog, mw, c, lane);
                     if (c >= 2) mbar_wait(&p_empty[pb], ((c >> 1) - 1) & 1, 400 + c);
                     tc_fence_after();
                     if (lane == 0) TL(1, c);

@@ -49,10 +49,11 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
     uint64_t* w_full = b_empty + S;                                // [2]   window piece written
     uint64_t* w_empty = w_full + 2;                                // [2]   window piece consumed
     uint64_t* m_full = w_empty + 2;                                // [MB]  fused-intermediate piece written
-    uint64_t* m_empty = m_full + 2;                                // [MB]  ... consumed
+    uint64_t* m_empty = m_full + 2;                                // [2]   ... consumed; indexed by the drain group that writes the freed buffer NEXT
     uint64_t* p_full = m_empty + 2;                                // [NPB] TMEM partial complete
     uint64_t* p_empty = p_full + NPB;                              // [NPB] TMEM partial drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + NPB);
+    volatile int* mma_prog = reinterpret_cast<volatile int*>(smem_raw + 496);   // [2] see mma_wait_turn (tc_kernels.cuh)
     float* bst = reinterpret_cast<float*>(smem_raw + 512);        // up to 40 barriers + the TMEM slot live in the first 512 B
     const int wrows = TT + (a.Ktaps - 1) * a.dil;
     const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
@@ -68,8 +69,10 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], 2); }
-        for (int i = 0; i < MB; ++i) { mbar_init(&m_full[i], HALF ? 256 : 128); mbar_init(&m_empty[i], 2); }
+        for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
+        for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], 2);
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
+        mma_prog[0] = -1; mma_prog[1] = -1;
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -125,7 +128,9 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
         const uint32_t wbuf0_u = smem_u32(wbuf0), wbuf1_u = smem_u32(wbuf1), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
         auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off) {
             const int s = c % S, pb = c % NPB;
+            mma_wait_turn<S>(mma_prog, mw, c);
             mbar_wait(&b_full[s], (c / S) & 1, 300);
+            mma_publish<S>(mma_prog, mw, c, lane);
             if (c >= NPB) mbar_wait(&p_empty[pb], ((c / NPB) - 1) & 1, 400);
             tc_fence_after();
             if (lane == 0) TLP(1, c - c_tile0);
@@ -170,7 +175,9 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
                 const uint32_t m_hi = mbuf_u + (uint32_t)mb * (2u * CP * MIDP * 4u);
                 if ((c & 1) == mw) issue_group(m_hi, m_hi + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
-                if (elect_one()) umma_commit(&m_empty[mb]);
+                // buffer mb is free for piece mp + MB, which drain group (mp + MB) % NDG writes: signal THAT group's barrier, so
+                // that every m_empty barrier has one group of waiters which sees each of its phases exactly once, in order
+                if (elect_one()) umma_commit(&m_empty[HALF ? 0 : (mp + MB) % NDG]);
                 __syncwarp();
             }
         };
@@ -315,7 +322,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
         constexpr bool PREFETCH_RES = FUSE && NT <= 64;     // registers permitting
         float4 rpre[PREFETCH_RES ? PPG : 1][UC / 4];
         int c = 0, mq = 0, ti = -1, c_tile0 = 0;
-        int m_seen[2] = {0, 0};
+        int m_waits = 0;
         auto drain = [&](float (&acc)[NCOL], int ngroups) {
             for (int gi = 0; gi < ngroups; ++gi, ++c) {
                 const int pb = c % NPB;
@@ -373,14 +380,14 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                     const float4 m4 = apply_act_t<PRE>(make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]), a.slope);
                     racc[i] = m4.x; racc[i + 1] = m4.y; racc[i + 2] = m4.z; racc[i + 3] = m4.w;
                 }
-                // intermediate pieces in consumption order 0,1,2,...: piece q is written by group q % NDG into buffer
-                // Q % MB (Q = running piece index), which is free once piece Q-MB was consumed = completion #(Q/MB - 1) of
-                // that buffer's m_empty.  Every thread walks through all completions of both buffers in order.
+                // intermediate pieces in consumption order 0,1,2,...: piece q is written by group q % NDG (both groups at NT=32)
+                // into buffer Q % MB (Q = running piece index), which is free once piece Q-MB was consumed; the MMA warps signal
+                // that on the writing group's own m_empty barrier, so the k-th wait of a thread is for that barrier's k-th phase.
 #pragma unroll
                 for (int q = 0; q < NT / CP; ++q) {
                     const int Q = mq + q, mb = Q % MB;
-                    while (m_seen[mb] < Q / MB) { mbar_wait(&m_empty[mb], m_seen[mb] & 1, 700); ++m_seen[mb]; }
                     if (HALF || q % NDG == dg) {
+                        if (Q >= MB) { mbar_wait(&m_empty[HALF ? 0 : dg], m_waits & 1, 700); ++m_waits; }
                         const int pl = HALF ? 0 : q / NDG;
                         float* hi = mbuf + mb * (2 * CP * MIDP);
                         float* lo = hi + CP * MIDP;

@@ -101,6 +101,7 @@ template <int S> __device__ __forceinline__ void mma_wait_turn(volatile int* pro
         long long t0 = 0;
         unsigned spins = 0;
         while (prog[mw ^ 1] < c - S) {
+            __nanosleep(64);        // a hot spin here steals issue slots from the producer/drain warps of the same sub-partition (measured: -10..20 %)
             if ((++spins & 0xfffu) == 0) {
                 if (t0 == 0) t0 = clock64();
                 else if (clock64() - t0 > 4000000000ll) { printf("adec: MMA warp order wait timed out: group %d\n", c); __trap(); }

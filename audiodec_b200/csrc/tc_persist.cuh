@@ -16,14 +16,18 @@
 namespace adec {
 
 template <int NT> struct TcpCfg {
-    static constexpr int NPB = NT == 128 ? 4 : 8;          // TMEM partial buffers (NPB*NT <= 512 columns): how far the MMAs run ahead
 #ifdef ADEC_ALT_NT64
     static constexpr int MB = 1;
     static constexpr int STAGES = NT == 64 ? 6 : TcCfg<NT>::STAGES;
 #else
     static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128)
-    static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages (8 stages at NT=32 measured no faster)
+    static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages (at NT=32: 4 stages measured 13 % SLOWER than 3, 8 no faster)
 #endif
+    // MMA issuer warps take groups c = 0,1,2,... round robin.  Every mbarrier must have waiters that see each of its phases in
+    // order (a parity wait cannot tell phase k from phase k-2), so a weight stage (c % STAGES) and a TMEM partial (c % NPB) must
+    // always belong to the same warp: NW divides both.  Odd ring depth -> three issuer warps.
+    static constexpr int NW = (STAGES % 2) ? 3 : 2;
+    static constexpr int NPB = NT == 128 ? (NW == 3 ? 3 : 4) : (NW == 3 ? 6 : 8);   // TMEM partial buffers (NPB*NT <= 512 columns): how far the MMAs run ahead
     static constexpr int NDG = NT == 32 ? 2 : TcCfg<NT>::NDG;          // drain groups; at NT=32 each owns HALF a 32-column piece
     static constexpr int THREADS = 128 + TcCfg<NT>::NPROD + 128 * NDG;
 };
@@ -41,7 +45,10 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
     constexpr bool PIPE = FUSE && NT == 32;              // conv of tile i+1 issued before the 1x1 conv of tile i (needs 2*NCOL drain registers;
                                                          // measured: -19 % at NT=32, +3 % (register spills) at NT=64)
     constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    constexpr uint32_t TMEM_COLS = NPB * NT;
+    constexpr int NW = TcpCfg<NT>::NW;
+    static_assert(S % NW == 0 && NPB % NW == 0, "a weight stage / TMEM partial must belong to one MMA warp");
+    constexpr uint32_t TMEM_COLS = NPB * NT <= 32 ? 32 : NPB * NT <= 64 ? 64 : NPB * NT <= 128 ? 128 : NPB * NT <= 256 ? 256 : 512;   // power of two
+    static_assert(NPB * NT <= 512, "TMEM has 512 columns");
 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);     // [S]   weights landed
@@ -53,7 +60,6 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
     uint64_t* p_full = m_empty + 2;                                // [NPB] TMEM partial complete
     uint64_t* p_empty = p_full + NPB;                              // [NPB] TMEM partial drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + NPB);
-    volatile int* mma_prog = reinterpret_cast<volatile int*>(smem_raw + 496);   // [2] see mma_wait_turn (tc_kernels.cuh)
     float* bst = reinterpret_cast<float*>(smem_raw + 512);        // up to 40 barriers + the TMEM slot live in the first 512 B
     const int wrows = TT + (a.Ktaps - 1) * a.dil;
     const int wrp = (wrows > MIDP ? wrows : MIDP) | 1;             // odd row pitch: conflict-free producer stores
@@ -68,11 +74,10 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], 2); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], NW); }
         for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
-        for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], 2);
+        for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], NW);
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
-        mma_prog[0] = -1; mma_prog[1] = -1;
         mbar_fence_init();
     }
     if (warp == 0) {
@@ -119,8 +124,8 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 }
             }
         }
-    } else if (warp == 1 || warp == 2) {
-        // ------------------------------------------------ MMA issuers (alternate groups)
+    } else if (warp >= 1 && warp <= NW) {
+        // ------------------------------------------------ MMA issuers (groups round robin)
         const int mw = warp - 1;
         int c = 0, wp = 0, mp = 0;
         int ti = -1, c_tile0 = 0;
@@ -128,9 +133,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
         const uint32_t wbuf0_u = smem_u32(wbuf0), wbuf1_u = smem_u32(wbuf1), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
         auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off) {
             const int s = c % S, pb = c % NPB;
-            mma_wait_turn<S>(mma_prog, mw, c);
             mbar_wait(&b_full[s], (c / S) & 1, 300);
-            mma_publish<S>(mma_prog, mw, c, lane);
             if (c >= NPB) mbar_wait(&p_empty[pb], ((c / NPB) - 1) & 1, 400);
             tc_fence_after();
             if (lane == 0) TLP(1, c - c_tile0);
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 const uint32_t a_hi = buf ? wbuf1_u : wbuf0_u;
                 const uint32_t a_lo = a_hi + (uint32_t)(CP / 4) * lbo1;
                 for (int tap = 0; tap < a.Ktaps; ++tap, ++c)
-                    if ((c & 1) == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)(tap * a.dil) * 16u);
+                    if (c % NW == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)(tap * a.dil) * 16u);
                 if (elect_one()) umma_commit(&w_empty[buf]);
                 __syncwarp();
             }
@@ -174,7 +177,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                 const int mb = mp % MB;
                 mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
                 const uint32_t m_hi = mbuf_u + (uint32_t)mb * (2u * CP * MIDP * 4u);
-                if ((c & 1) == mw) issue_group(m_hi, m_hi + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
+                if (c % NW == mw) issue_group(m_hi, m_hi + (uint32_t)(CP / 4) * lbo2, lbo2, 0u);
                 // buffer mb is free for piece mp + MB, which drain group (mp + MB) % NDG writes: signal THAT group's barrier, so
                 // that every m_empty barrier has one group of waiters which sees each of its phases exactly once, in order
                 if (elect_one()) umma_commit(&m_empty[HALF ? 0 : (mp + MB) % NDG]);

@@ -278,7 +278,7 @@ def run_ours(args):
         "conv_path": conv_path,
         "clocks": clocks,
     }
-    if args.cpu_baseline:
+    if args.cpu_baseline and world == 1:          # reported at N=1 only (rank 0); the reference arm covers every N
         line["cpu_baseline"] = cpu_baseline(args.workload, n_utt=args.cpu_utts, threads=best_cpu_threads(args.workload))
     print(json.dumps(line), flush=True)
 

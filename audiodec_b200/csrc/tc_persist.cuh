@@ -5,11 +5,16 @@
 // into the next:
 //     producers   : run ahead on the next tile's activation window while the current tile is in its 1x1 conv / epilogue
 //     TMA         : keeps the weight ring full across tile boundaries
-//     MMA (2 warps): GEMM 1 of tile i+1 starts as soon as its window piece and a TMEM partial are free
-//     drain       : four TMEM partials (instead of two) let the MMAs run ahead while these warps convert the fused
+//     MMA (2-3 warps, groups round robin): GEMM 1 of tile i+1 starts as soon as its window piece and a TMEM partial are free;
+//                   at NT=32 it is even issued BEFORE the 1x1 conv of tile i (PIPE)
+//     drain       : 3-8 TMEM partials (instead of two) let the MMAs run ahead while these warps convert the fused
 //                   intermediate or write the epilogue
-// The fused intermediate has its own smem buffer and barrier pair (m_full/m_empty) so that each barrier is waited on
-// by threads that observe every one of its phases (an mbarrier parity wait is only unambiguous for such a waiter).
+// Barrier rule: an mbarrier parity wait cannot tell phase k from phase k-2, so every barrier here has
+// waiters that observe each of its phases in order and can never fall two phases behind:
+//     b_full[s] / p_empty[pb] : stage s = c % STAGES and partial pb = c % NPB always belong to the same issuer warp (NW divides both)
+//     m_empty[g]              : "intermediate buffer free" is signalled to the drain group that writes that buffer NEXT
+//     w_full/w_empty, m_full, p_full, b_empty : every waiter waits for every phase, and a phase cannot complete before all of
+//                               them consumed the previous one
 #pragma once
 #include "tc_kernels.cuh"
 

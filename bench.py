@@ -341,9 +341,9 @@ def run_reference(args):
     world = int(os.environ.get("WORLD_SIZE", 1))
     best_cpu_threads(args.workload)
     per = []
-    n_utt = 16                                  # ~1 s of host work per step on the box's cores: K=10 steps stay well under a minute
+    n_utt = args.ref_utts                       # 16: ~1 s of host work per step on the box's cores, K=10 steps stay well under a minute
     for _ in range(args.warmup):
-        cpu_baseline(args.workload, n_utt=2)
+        cpu_baseline(args.workload, n_utt=min(2, n_utt))
     t_all0 = time.perf_counter()
     last = None
     for _ in range(args.steps):
@@ -379,6 +379,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
     ap.add_argument("--cpu-utts", type=int, default=192,
                     help="utterances of the bounded CPU sample (192 x 1 s = three steps' worth of audio, 10-15 s of host work)")
+    ap.add_argument("--ref-utts", type=int, default=16, help="--impl reference: utterances per step (each step time-bounded at 15 s)")
     ap.add_argument("--breakdown", action="store_true", help="print per-launch CUDA-event times to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -5,6 +5,7 @@ import ctypes
 import os
 import re
 import socket
+import subprocess
 import sys
 
 import pytest
@@ -170,3 +171,33 @@ def test_c_rvq_oracle_matches_torch_bitwise():
     same = (od[0] == dist0.numpy()).mean()
     assert same > 0.999, f"only {same:.4f} of the fp32 distances are bit-identical on this CPU"
     np.testing.assert_allclose(ozq, zq[0].numpy(), atol=1e-6)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference runs on the host alone (oracle port) and prints ONE JSON line with the keys the
+    driver reads; under torchrun only rank 0 prints."""
+    import json
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-utts", "1"]
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+    # a non-zero rank exits 0 without printing
+    out = subprocess.run(cmd, capture_output=True, text=True, env=dict(env, RANK="1", WORLD_SIZE="2"), timeout=600)
+    assert out.returncode == 0 and not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_bench_cuda_arm_fails_loudly_without_a_gpu():
+    out = subprocess.run([sys.executable, os.path.join(REPO, "bench.py"), "--steps", "1", "--warmup", "3", "--no-cpu-baseline"],
+                         capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), timeout=600)
+    assert out.returncode != 0
+    assert not [l for l in out.stdout.splitlines() if l.startswith("{")]

@@ -58,6 +58,10 @@ SYMBOLS = {
     "adec_frames_for": (c_int, [c_void_p, c_int]),
     "adec_hop_length": (c_int, [c_void_p]),
     "adec_codec_host": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "adec_packed_frame_bytes": (c_int, [c_void_p]),
+    "adec_pack_indices": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "adec_unpack_indices": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "adec_index_error": (c_int, [c_void_p, c_void_p]),
     "adec_launch_count": (c_int64, [c_void_p]),
     "adec_profile": (c_int, [c_void_p, c_int]),
     "adec_profile_report": (c_int, [c_void_p, c_char_p, c_int]),

@@ -214,6 +214,47 @@ class SymADStreamGenerator(_StreamGeneratorBase):
         _check(self._lib.adec_lookup(self._h, _ptr(idx), b, f, _ptr(zq), self._stream()), self._h)
         return zq
 
+    # ---- index bitstream (the reference queues the raw int64 tensor, bin/stream.py:224)
+    def packed_frame_bytes(self):
+        self._ready()
+        return self._lib.adec_packed_frame_bytes(self._h)
+
+    def pack(self, idx):
+        """idx (Nq,F) -> uint8 (F,bytes); (Nq,B,F) -> (B,F,bytes): Nq x ceil(log2 N)-bit local indices per frame."""
+        self._ready()
+        idx = self._in(idx, torch.int64)
+        two_d = idx.dim() == 2
+        if two_d:
+            idx = idx.unsqueeze(1)
+        nq, b, f = idx.shape
+        if nq != self.codebook_num:
+            raise RuntimeError(f"audiodec_b200: pack: expected {self.codebook_num} index rows, got {nq}")
+        out = torch.empty(b, f, self.packed_frame_bytes(), device=self._device, dtype=torch.uint8)
+        _check(self._lib.adec_pack_indices(self._h, _ptr(idx), b, f, _ptr(out), self._stream()), self._h)
+        return out.squeeze(0) if two_d else out
+
+    def unpack(self, packed):
+        """uint8 (F,bytes) -> idx (Nq,F); (B,F,bytes) -> (Nq,B,F) int64 flat indices, ready for lookup()."""
+        self._ready()
+        packed = self._in(packed, torch.uint8)
+        two_d = packed.dim() == 2
+        if two_d:
+            packed = packed.unsqueeze(0)
+        b, f, nb = packed.shape
+        if nb != self.packed_frame_bytes():
+            raise RuntimeError(f"audiodec_b200: unpack: expected {self.packed_frame_bytes()} bytes per frame, got {nb}")
+        idx = torch.empty(self.codebook_num, b, f, device=self._device, dtype=torch.int64)
+        _check(self._lib.adec_unpack_indices(self._h, _ptr(packed), b, f, _ptr(idx), self._stream()), self._h)
+        return idx.squeeze(1) if two_d else idx
+
+    def index_error(self):
+        """True if lookup / pack / unpack met an out-of-range index since the last call (synchronises the stream)."""
+        self._ready()
+        rc = self._lib.adec_index_error(self._h, self._stream())
+        if rc < 0:
+            raise RuntimeError("audiodec_b200: " + _lib.last_error(self._h))
+        return bool(rc)
+
     def decode(self, zq):
         """zq (B,F,D) channels-last -> y (B,1,F*hop)   (AudioDec.py:246-247)"""
         self._ready()

@@ -1208,6 +1208,51 @@ int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int
     return 0;
 }
 
+static int index_bits(int n) { int b = 1; while ((1 << b) < n) ++b; return b; }
+
+int adec_packed_frame_bytes(const adec_handle* h) {
+    if (!h || h->cfg.model_type != ADEC_MODEL_SYMAD) return -1;
+    return (h->cfg.codebook_num * index_bits(h->cfg.codebook_size) + 7) / 8;
+}
+
+static int pack_common(adec_handle* h, const char* what, int64_t* idx, int B, int F, uint8_t* packed, void* stream, bool pack) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail(std::string(what) + ": not a symAD handle");
+    if (B < 1 || F < 1) return h->fail(std::string(what) + ": empty input");
+    if (h->cfg.codebook_size < 2 || h->cfg.codebook_size > 65536) return h->fail(std::string(what) + ": codebook_size must be in [2, 65536]");
+    DeviceGuard dg(h->device);
+    PackArgs a{};
+    a.idx = (long long*)idx; a.packed = packed; a.nfr = (long long)B * F; a.nq = h->cfg.codebook_num; a.N = h->cfg.codebook_size;
+    a.bits = index_bits(a.N); a.bpf = adec_packed_frame_bytes(h); a.err = h->d_err;
+    const unsigned grid = (unsigned)((a.nfr + 255) / 256);
+    if (pack) pack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    else unpack_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+    CK(h, cudaGetLastError());
+    ++h->launches;
+    return 0;
+}
+
+int adec_pack_indices(adec_handle* h, const int64_t* idx, int B, int F, uint8_t* packed, void* stream) {
+    return pack_common(h, "pack_indices", const_cast<int64_t*>(idx), B, F, packed, stream, true);
+}
+
+int adec_unpack_indices(adec_handle* h, const uint8_t* packed, int B, int F, int64_t* idx, void* stream) {
+    return pack_common(h, "unpack_indices", idx, B, F, const_cast<uint8_t*>(packed), stream, false);
+}
+
+int adec_index_error(adec_handle* h, void* stream) {
+    if (!h || !h->d_err) return -1;
+    DeviceGuard dg(h->device);
+    int herr = 0;
+    if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess ||
+        cudaMemcpy(&herr, h->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) {
+        h->fail("index_error: CUDA error while reading the flag");
+        return -1;
+    }
+    return herr;
+}
+
 int64_t adec_launch_count(const adec_handle* h) { return h ? h->launches : 0; }
 
 int adec_profile(adec_handle* h, int enable) {

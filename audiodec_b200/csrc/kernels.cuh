@@ -649,6 +649,49 @@ __global__ void __launch_bounds__(256) lookup_kernel(const LookupArgs a) {
     *reinterpret_cast<float4*>(a.zq + fr * a.D + k4) = s;
 }
 
+// Index bitstream.  The reference has no wire format: it ships int64 (Nq,F) tensors through a queue
+// (bin/stream.py:224).  Packed frame = Nq local indices (idx - i*N) of `bits` = ceil(log2 N) bits each, stage 0 first, little-endian
+// bit order, zero-padded to whole bytes: 8 x 10 bit = 10 bytes per frame.  One thread per frame (a frame is 10-20 bytes).
+struct PackArgs {
+    long long* idx;           // (nq, nfr) flat indices (+N*i), read by pack / written by unpack
+    unsigned char* packed;    // (nfr, bpf)
+    long long nfr;
+    int nq, N, bits, bpf;
+    int* err;                 // set to 1 on an out-of-range index / code
+};
+
+__global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
+    const long long fr = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (fr >= a.nfr) return;
+    unsigned char* o = a.packed + fr * a.bpf;
+    unsigned long long acc = 0;
+    int nb = 0, ob = 0;
+    for (int i = 0; i < a.nq; ++i) {
+        long long v = a.idx[(long long)i * a.nfr + fr] - (long long)i * a.N;
+        if (v < 0 || v >= a.N) { *a.err = 1; v = 0; }
+        acc |= (unsigned long long)v << nb;
+        nb += a.bits;
+        while (nb >= 8) { o[ob++] = (unsigned char)(acc & 0xffu); acc >>= 8; nb -= 8; }
+    }
+    if (nb > 0) o[ob++] = (unsigned char)(acc & 0xffu);
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const PackArgs a) {
+    const long long fr = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (fr >= a.nfr) return;
+    const unsigned char* in = a.packed + fr * a.bpf;
+    const unsigned long long mask = (1ull << a.bits) - 1ull;
+    unsigned long long acc = 0;
+    int nb = 0, ib = 0;
+    for (int i = 0; i < a.nq; ++i) {
+        while (nb < a.bits) { acc |= (unsigned long long)in[ib++] << nb; nb += 8; }
+        long long v = (long long)(acc & mask);
+        acc >>= a.bits; nb -= a.bits;
+        if (v >= a.N) { *a.err = 1; v = 0; }
+        a.idx[(long long)i * a.nfr + fr] = v + (long long)i * a.N;
+    }
+}
+
 // replicate stream 0's state to all streams (adec_set_streams)
 __global__ void replicate_kernel(float* dst, const float* src, long long per_stream, int n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

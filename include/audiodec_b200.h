@@ -109,6 +109,18 @@ int adec_hop_length(const adec_handle *h);
 int adec_codec_host(adec_handle *enc, adec_handle *dec, const float *x_host, int B, int T,
                     int64_t *idx_host, float *y_host, void *stream);
 
+/* -- index bitstream -------------------------------------------------- */
+/* The reference has no wire format: AudioCodecStreamer ships the int64 (Nq,F) index tensor through a queue
+ * (bin/stream.py:224).  Packed frame = Nq local indices (idx - i*codebook_size) of ceil(log2 codebook_size) bits each,
+ * stage 0 first, little-endian bit order, zero-padded to whole bytes: 8 x 10 bit = 10 bytes / frame = 12.8 kbit/s at
+ * hop 300 / 48 kHz.  idx (Nq,B,F) int64 flat <-> packed (B,F,adec_packed_frame_bytes) uint8, device pointers. */
+int adec_packed_frame_bytes(const adec_handle *h);       /* -1 if h is not a symAD handle */
+int adec_pack_indices(adec_handle *h, const int64_t *idx, int B, int F, uint8_t *packed, void *stream);
+int adec_unpack_indices(adec_handle *h, const uint8_t *packed, int B, int F, int64_t *idx, void *stream);
+/* synchronises `stream`, then returns and clears the handle's device-side flag: 1 if lookup / pack / unpack met an
+ * out-of-range index since the last call (the reference's F.embedding would have raised, vq_module.py:160), -1 on error */
+int adec_index_error(adec_handle *h, void *stream);
+
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t adec_launch_count(const adec_handle *h);
 

@@ -160,3 +160,26 @@ def test_released_variants(golden_dir, fname):
     outs = [c.run(x[:, :, i:i + 3200]) for i in (0, 3200)]
     np.testing.assert_array_equal(torch.cat([o[1] for o in outs], -1).numpy(), g["idx_chunks"])
     np.testing.assert_allclose(torch.cat([o[3] for o in outs], -1).numpy(), g["y_chunks"], atol=TOL)
+
+
+def test_bitstream_oracle_known_answer_and_round_trip():
+    """oracle/bitstream_oracle.py against an independent statement of the same format (one little-endian big integer per
+    frame) and its own inverse; frame sizes of the released configs."""
+    from oracle import bitstream_oracle as BO
+    assert BO.index_bits(1024) == 10 and BO.index_bits(1000) == 10 and BO.index_bits(2) == 1
+    assert BO.frame_bytes(8, 1024) == 10 and BO.frame_bytes(16, 1024) == 20 and BO.frame_bytes(3, 1024) == 4
+    rng = np.random.default_rng(0)
+    for nq, n in ((8, 1024), (16, 1024), (3, 1000), (5, 7)):
+        idx = rng.integers(0, n, (nq, 2, 6)) + n * np.arange(nq)[:, None, None]
+        packed = BO.pack_indices(idx, n)
+        bits = BO.index_bits(n)
+        for b in range(2):
+            for f in range(6):
+                big = 0
+                for i in range(nq):
+                    big |= int(idx[i, b, f] - i * n) << (bits * i)
+                assert bytes(packed[b, f]) == big.to_bytes(BO.frame_bytes(nq, n), "little")
+        np.testing.assert_array_equal(BO.unpack_indices(packed, nq, n), idx)
+    # hand-computed vector: local indices 1..8, 10 bits each
+    idx = (np.arange(8) + 1 + 1024 * np.arange(8)).reshape(8, 1, 1)
+    assert BO.pack_indices(idx, 1024).ravel().tolist() == [1, 8, 48, 0, 1, 5, 24, 112, 0, 2]

@@ -231,3 +231,56 @@ def test_released_variants_golden(golden_dir, fname):
     outs = [_run(tx, rx, dec, x[:, :, i:i + 3200]) for i in (0, 3200)]
     np.testing.assert_array_equal(torch.cat([o[1] for o in outs], -1).numpy(), g["idx_chunks"])
     np.testing.assert_allclose(torch.cat([o[3] for o in outs], -1).numpy(), g["y_chunks"], atol=WAVE_TOL)
+
+
+def test_index_bitstream_matches_oracle_and_round_trips(symad_sd):
+    """Nq x 10-bit packed frames.  The pack kernel reproduces the numpy oracle's bytes, unpack inverts it
+    bit-exactly on indices the quantiser really emits (ragged B x F), and the decoded audio is unchanged by the round trip."""
+    from oracle import bitstream_oracle as BO
+    tx, rx, dec, _ = _codec(symad_sd)
+    torch.manual_seed(11)
+    z = 0.6 * torch.randn(3, 64, 37)
+    idx = tx.quantize(z.cuda())                                    # (8,3,37)
+    assert tx.packed_frame_bytes() == BO.frame_bytes(8, 1024) == 10
+    packed = tx.pack(idx)
+    assert packed.dtype == torch.uint8 and tuple(packed.shape) == (3, 37, 10)
+    np.testing.assert_array_equal(packed.cpu().numpy(), BO.pack_indices(idx.cpu().numpy(), 1024))
+    back = rx.unpack(packed)
+    assert back.dtype == torch.int64
+    np.testing.assert_array_equal(back.cpu().numpy(), idx.cpu().numpy())
+    np.testing.assert_array_equal(rx.lookup(back).cpu().numpy(), rx.lookup(idx).cpu().numpy())
+    assert not tx.index_error() and not rx.index_error()
+    # B == 1 keeps the reference's 2-D (Nq,F) shape on both sides
+    idx1 = tx.quantize(z[:1].cuda())
+    p1 = tx.pack(idx1)
+    assert tuple(idx1.shape) == (8, 37) and tuple(p1.shape) == (37, 10)
+    np.testing.assert_array_equal(rx.unpack(p1).cpu().numpy(), idx1.cpu().numpy())
+    # extremes: all-zero and all-max local indices
+    for v in (0, 1023):
+        e = (torch.full((8, 2, 5), v, dtype=torch.int64) + 1024 * torch.arange(8).view(8, 1, 1)).cuda()
+        pe = tx.pack(e)
+        np.testing.assert_array_equal(pe.cpu().numpy(), BO.pack_indices(e.cpu().numpy(), 1024))
+        np.testing.assert_array_equal(rx.unpack(pe).cpu().numpy(), e.cpu().numpy())
+    # an index outside its stage's range is flagged (the reference's F.embedding would raise), then the flag clears
+    bad = idx.clone()
+    bad[3, 1, 2] = 5 * 1024 + 7                                     # stage-3 row holding a stage-5 index
+    tx.pack(bad)
+    assert tx.index_error() and not tx.index_error()
+    bad[3, 1, 2] = 8 * 1024 + 1
+    rx.lookup(bad)
+    assert rx.index_error() and not rx.index_error()
+
+
+def test_index_bitstream_16_codebooks():
+    """symAD_c16 (16 codebooks, hop 320): 16 x 10 bit = 20 bytes / frame = 24 kbit/s at 48 kHz."""
+    from audiodec_b200.codec import SymADStreamGenerator
+    from oracle import bitstream_oracle as BO
+    g = SymADStreamGenerator(**S.SYMAD_C16_PARAMS)
+    g.load_state_dict(S.symad_state_dict(S.SYMAD_C16_PARAMS, seed=0))
+    g = g.eval().to(torch.device("cuda:0"))
+    rng = np.random.default_rng(5)
+    idx = rng.integers(0, 1024, (16, 2, 9)) + 1024 * np.arange(16)[:, None, None]
+    p = g.pack(torch.from_numpy(idx).cuda())
+    assert tuple(p.shape) == (2, 9, 20)
+    np.testing.assert_array_equal(p.cpu().numpy(), BO.pack_indices(idx, 1024))
+    np.testing.assert_array_equal(g.unpack(p).cpu().numpy(), idx)

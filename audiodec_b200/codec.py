@@ -214,6 +214,33 @@ class SymADStreamGenerator(_StreamGeneratorBase):
         _check(self._lib.adec_lookup(self._h, _ptr(idx), b, f, _ptr(zq), self._stream()), self._h)
         return zq
 
+    # ---- non-streaming batch forward (codecTest.py:78-95).  These calls discard the streaming state.
+    def encode_offline(self, x):
+        """x (B,1,T) -> z (B,code_dim,F): Encoder.forward + Projector.forward, zero left-pad (conv_layer.py:148-151)."""
+        self._ready()
+        x = self._in(x)
+        b, _, t = x.shape
+        f = self._lib.adec_frames_for(self._h, t)
+        z = torch.empty(b, self.code_dim, f, device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_encode_offline(self._h, _ptr(x), b, t, _ptr(z), self._stream()), self._h)
+        return z
+
+    def quantize_offline(self, z):
+        """z (B,code_dim,F) -> (zq (B,code_dim,F) channels-first like Quantizer.forward (quantizer.py:31-34), idx (Nq,B,F))."""
+        self._ready()
+        z = self._in(z)
+        b, _, f = z.shape
+        idx = torch.empty(self.codebook_num, b, f, device=self._device, dtype=torch.int64)
+        _check(self._lib.adec_quantize(self._h, _ptr(z), b, f, _ptr(idx), self._stream()), self._h)
+        zq = torch.empty(b, f, self.code_dim, device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_lookup(self._h, _ptr(idx), b, f, _ptr(zq), self._stream()), self._h)
+        return zq.transpose(1, 2), idx
+
+    def decode_offline(self, zq):
+        """zq (B,code_dim,F) channels-first (what Decoder.forward takes, decoder.py:135-140) -> y (B,1,F*hop); transposed convs
+        replicate their first input frame (conv_layer.py:189-192)."""
+        return _decode_offline(self, zq)
+
     # ---- index bitstream (SURVEY.md 8(f) rank 2; the reference queues the raw int64 tensor, bin/stream.py:224)
     def packed_frame_bytes(self):
         self._ready()
@@ -266,6 +293,16 @@ class SymADStreamGenerator(_StreamGeneratorBase):
         return y
 
 
+def _decode_offline(gen, zq):
+    gen._ready()
+    zq = gen._in(zq)
+    b, _, f = zq.shape
+    zq_cl = zq.transpose(1, 2).contiguous()                       # the kernels' native channels-last (B,F,D)
+    y = torch.empty(b, 1, f * gen._lib.adec_hop_length(gen._h), device=gen._device, dtype=torch.float32)
+    _check(gen._lib.adec_decode_offline(gen._h, _ptr(zq_cl), b, f, _ptr(y), gen._stream()), gen._h)
+    return y
+
+
 class HiFiGANStreamGenerator(_StreamGeneratorBase):
     """models/vocoder/HiFiGAN.py:222-305 (AD v1: groups>1 and a single resblock kernel -> MultiGroupConv1d)."""
 
@@ -313,6 +350,32 @@ class HiFiGANStreamGenerator(_StreamGeneratorBase):
         y = torch.empty(b, 1, f * self._lib.adec_hop_length(self._h), device=self._device, dtype=torch.float32)
         _check(self._lib.adec_decode(self._h, _ptr(c), b, f, _ptr(y), self._stream()), self._h)
         return y
+
+    def forward(self, c):
+        """Generator.forward (HiFiGAN.py:140-160), the non-streaming path: c (B,in_channels,F) channels-first -> y (B,1,F*hop).
+        Discards the streaming state."""
+        return _decode_offline(self, c)
+
+    __call__ = forward
+
+
+class OfflineCodec:
+    """Mirror of codecTest.py's TestMain.encode / decode (codecTest.py:78-95): the non-streaming batch path.
+    `encoder` is a SymADStreamGenerator, `decoder` a SymADStreamGenerator or HiFiGANStreamGenerator, both already on a
+    CUDA device; they must not be the handles a live stream is using (offline calls reset the causal state)."""
+
+    def __init__(self, encoder, decoder, multi_channel=False):
+        self.encoder, self.decoder, self.multi_channel = encoder, decoder, multi_channel
+
+    def encode(self, audio):
+        """audio (T,C) float array -> zq (C,code_dim,F) (or (1,code_dim,F) when multi_channel)."""
+        x = torch.as_tensor(audio, dtype=torch.float32).to(self.encoder._device)
+        x = x.transpose(1, 0).unsqueeze(0) if self.multi_channel else x.transpose(1, 0).unsqueeze(1)
+        zq, _ = self.encoder.quantize_offline(self.encoder.encode_offline(x))
+        return zq
+
+    def decode(self, zq):
+        return self.decoder.forward(zq) if isinstance(self.decoder, HiFiGANStreamGenerator) else self.decoder.decode_offline(zq)
 
 
 def codec_host(encoder: SymADStreamGenerator, decoder, x_host: torch.Tensor, want_idx=True, reuse_buffers=False):

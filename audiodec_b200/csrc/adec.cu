@@ -227,6 +227,7 @@ struct adec_handle {
     std::set<std::string> consumed;
     std::vector<Op> enc_ops, dec_ops;
     int n_streams = 1;
+    int st_cap = 1;        // streams the state buffers were allocated for
     bool use_tc = true;           // ADEC_CONV_PATH=ffma selects the CUDA-core kernels
     int persist_mask = 32 | 64 | 128;  // ADEC_TC_PERSIST: bit mask of channel-tile widths (32|64|128) that use the persistent kernel
     int n_sms = 148;
@@ -555,6 +556,7 @@ struct RunCtx {
     const float* ext_in;
     float* ext_out;
     cudaStream_t stream;
+    bool offline = false;   // non-streaming forward: transposed convs replicate their first input row instead of reading state
 };
 
 int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, int* T_out_final) {
@@ -614,6 +616,7 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.y = yout; a.ldy = op.ldy; a.y_goff = op.y_goff; a.out_nct = op.out_nct;
             a.y_bs = op.out_nct ? (long long)op.G * op.Cout * Tout : (long long)Tout * op.ldy;
             a.mid_act = op.mid_act;
+            a.hist_rep = (rc.offline && op.up > 1) ? 1 : 0;
             if (op.tc) {
                 const int wrows = TC_TT + (op.Ktaps - 1) * op.dil;
                 const int wrp = std::max(wrows, 129) | 1;
@@ -1106,7 +1109,27 @@ int adec_set_streams(adec_handle* h, int n) {
         }
     CK(h, cudaDeviceSynchronize());
     h->n_streams = n;
+    h->st_cap = n;
     return 0;
+}
+
+// Non-streaming forward (codecTest.py:78-95): any batch size, every causal conv starts from a zero left-pad
+// (conv_layer.py:148-151) = zeroed state for exactly B streams.  Discards the handle's streaming state.
+static int offline_state(adec_handle* h, int B, cudaStream_t s) {
+    if (B > h->st_cap) {
+        CK(h, cudaDeviceSynchronize());
+        for (auto* ops : {&h->enc_ops, &h->dec_ops})
+            for (Op& op : *ops) {
+                const size_t per = (size_t)op.P * op.st_C;
+                if (!per) continue;
+                for (int i = 0; i < 2; ++i)
+                    if (dev_alloc(h, &op.st[i], per * B)) return 1;     // old buffers stay in `owned` until destroy
+                op.cur = 0;
+            }
+        h->st_cap = B;
+    }
+    h->n_streams = B;
+    return adec_reset(h, (void*)s);
 }
 
 int adec_reset(adec_handle* h, void* stream) {
@@ -1144,6 +1167,25 @@ int adec_decode(adec_handle* h, const float* zq, int B, int F, float* y, void* s
     if (B < 1 || F < 1) return h->fail("decode: empty input");
     DeviceGuard dg(h->device);
     RunCtx rc{B, zq, y, (cudaStream_t)stream};
+    return run_ops(h, h->dec_ops, rc, F, nullptr);
+}
+
+int adec_encode_offline(adec_handle* h, const float* x, int B, int T, float* z, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail("encode_offline: not a symAD handle");
+    if (B < 1 || T < 1) return h->fail("encode_offline: empty input");
+    DeviceGuard dg(h->device);
+    if (offline_state(h, B, (cudaStream_t)stream)) return 1;
+    RunCtx rc{B, x, z, (cudaStream_t)stream, true};
+    return run_ops(h, h->enc_ops, rc, T, nullptr);
+}
+
+int adec_decode_offline(adec_handle* h, const float* zq, int B, int F, float* y, void* stream) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (B < 1 || F < 1) return h->fail("decode_offline: empty input");
+    DeviceGuard dg(h->device);
+    if (offline_state(h, B, (cudaStream_t)stream)) return 1;
+    RunCtx rc{B, zq, y, (cudaStream_t)stream, true};
     return run_ops(h, h->dec_ops, rc, F, nullptr);
 }
 

@@ -136,6 +136,8 @@ struct ConvArgs {
     long long y_bs;
     int ldy, y_goff, out_nct;
     int mid_act;         // FUSE: activation between the two GEMMs
+    int hist_rep;        // non-streaming forward of a transposed conv: history rows = the FIRST input row (ReplicationPad1d,
+                         // conv_layer.py:189-192) instead of the stored state
 };
 
 constexpr int CONV_STAGES = 4;
@@ -252,10 +254,11 @@ conv_gemm_kernel(const ConvArgs a) {
             if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
             const long long i = (long long)(j0 + m) * a.RG + r;     // x~ row
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (i < a.P) {
+            long long t = i - a.P;
+            if (a.hist_rep && t < 0) t = 0;
+            if (t < 0) {
                 v = *reinterpret_cast<const float4*>(sg + i * a.st_ld + ci);
             } else {
-                const long long t = i - a.P;
                 if (t < a.T) {
                     v = __ldg(reinterpret_cast<const float4*>(xg + t * a.ldx + ci));
                     if (a.pre_act == ACT_NORM) {

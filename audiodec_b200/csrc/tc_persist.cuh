@@ -261,8 +261,10 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                             const long long i = (long long)(j0 + m) * a.RG + r;
                             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (m < wrows) {
-                                if (i < a.P) v[u] = *reinterpret_cast<const float4*>(srow + i * a.st_ld);
-                                else if (i - a.P < a.T) v[u] = __ldg(reinterpret_cast<const float4*>(xrow + (i - a.P) * a.ldx));
+                                long long ti = i - a.P;
+                                if (a.hist_rep && ti < 0) ti = 0;              // non-streaming transposed conv: replicate the first input row
+                                if (ti < 0) v[u] = *reinterpret_cast<const float4*>(srow + i * a.st_ld);
+                                else if (ti < a.T) v[u] = __ldg(reinterpret_cast<const float4*>(xrow + ti * a.ldx));
                             }
                         }
 #pragma unroll
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(TcpCfg<NT>::THREADS, 1) tc_conv_persist_kernel
                             if (m < wrows) {
                                 const long long i = (long long)(j0 + m) * a.RG + r;
                                 float4 x4 = v[u];
-                                if (i >= a.P && i - a.P < a.T) {
+                                if ((i >= a.P || a.hist_rep) && i - a.P < a.T) {
                                     if (PRE == ACT_NORM) {
                                         const float4 mu = *reinterpret_cast<const float4*>(a.mean + ci);
                                         const float4 sc = *reinterpret_cast<const float4*>(a.scale + ci);

@@ -97,6 +97,15 @@ int adec_lookup(adec_handle *h, const int64_t *idx, int B, int F, float *zq, voi
 /* StreamGenerator.decode (AudioDec.py:246-247 / HiFiGAN.py:268-273): zq (B,F,code_dim) -> y (B,1,F*hop). */
 int adec_decode(adec_handle *h, const float *zq, int B, int F, float *y, void *stream);
 
+/* -- the non-streaming batch forward (codecTest.py:78-95, codecStatistic.py:92-98) ---------- */
+/* Encoder.forward + Projector.forward (models/autoencoder/modules/encoder.py:131, projector.py:49-50): every causal
+ * conv zero-pads on the left (layers/conv_layer.py:148-151) = no history; any batch size.  x (B,1,T) -> z (B,code_dim,F).
+ * DISCARDS the handle's streaming state (use a separate handle, or adec_reset + warm-up, before streaming again). */
+int adec_encode_offline(adec_handle *h, const float *x, int B, int T, float *z, void *stream);
+/* Decoder.forward (decoder.py:135-140) / HiFi-GAN Generator.forward (HiFiGAN.py:140-160): as above, and every transposed conv
+ * pads with its FIRST input frame (ReplicationPad1d, conv_layer.py:189-192).  zq (B,F,code_dim) channels-last -> y (B,1,F*hop). */
+int adec_decode_offline(adec_handle *h, const float *zq, int B, int F, float *y, void *stream);
+
 /* output frames of encode for T input samples: floor((T-1)/s)+1 applied per stride (conv_layer.py:153-156) */
 int adec_frames_for(const adec_handle *h, int T);
 /* product of the strides (utils/audiodec.py:58-62) */

@@ -111,6 +111,7 @@ class SymADOracle:
                 self.sd[base + "weight"] = fold_weight_norm(self.sd[k], self.sd[base + "weight_v"])
         # codec='activate_audiodec' (ActivateEncoder/ActivateDecoder, encoder.py:145-175, decoder.py:151-214)
         self.activate = self.p.get("codec", "audiodec") == "activate_audiodec"
+        self.offline = False          # forward_*: CausalConvTranspose1d.forward pads with the first frame (conv_layer.py:189-192)
         self.state = OrderedDict()
         self.reset_buffer()
         self.embeds = [self.sd[f"quantizer.codebook.layers.{i}.embed"] for i in range(self.p["codebook_num"])]
@@ -189,12 +190,33 @@ class SymADOracle:
                 h = F.elu(h)                             # decoder.py:207 conv_blocks[i][0]
             h, self.state[f"{n}.conv"] = causal_convtr1d_infer(
                 h, self.sd[f"{n}.conv.deconv.weight"], self.sd.get(f"{n}.conv.deconv.bias"),
-                self.state[f"{n}.conv"], s)
+                h[:, :, :1] if self.offline else self.state[f"{n}.conv"], s)
             for j, d in enumerate((1, 3, 9)):
                 h = self._res_unit(f"{n}.res_units.{j}", h, d)
         if self.activate:
             return torch.tanh(self._conv("decoder.conv2", F.elu(h)))      # decoder.py:209-211
         return self._conv("decoder.conv2", h)
+
+
+    # -- non-streaming forward (codecTest.py:78-95): CausalConv1d.forward zero-pads on the left (conv_layer.py:148-151), which
+    #    is inference() from an all-zero pad_buffer; CausalConvTranspose1d.forward replicates the first frame (:189-192)
+    def _offline_call(self, fn, arg):
+        self.reset_buffer()
+        self.offline = True
+        try:
+            return fn(arg)
+        finally:
+            self.offline = False
+            self.reset_buffer()
+
+    def forward_encode(self, x):                         # encoder.py:131 + projector.py:49-50 (codecTest.py:84-85)
+        return self._offline_call(self.encode, x)
+
+    def forward_quantize(self, z):                       # quantizer.py:31-34 -> vq_module.py:119-134 (eval: same quantize as :136-149)
+        return rvq_forward_index(z.transpose(2, 1), self.embeds)[0].transpose(2, 1)
+
+    def forward_decode(self, zq):                        # decoder.py:135-140 (codecTest.py:94); zq (B,D,F) channels-first
+        return self._offline_call(self.decode, zq.transpose(2, 1))
 
 
 # --------------------------------------------------------------------------- HiFi-GAN vocoder (AD v1)
@@ -215,6 +237,7 @@ class HiFiGANOracle:
         self.sd = sd
         self.mean, self.scale = sd.get("mean"), sd.get("scale")
         self.slope = self.p["nonlinear_activation_params"]["negative_slope"]
+        self.offline = False
         self.state = OrderedDict()
         self.reset_buffer()
 
@@ -245,9 +268,10 @@ class HiFiGANOracle:
         grp = self.p["groups"]
         for i, s in enumerate(self.p["upsample_scales"]):  # :287-291
             n = f"upsamples.{i}"
+            c = F.leaky_relu(c, self.slope)
             c, self.state[n] = causal_convtr1d_infer(
-                F.leaky_relu(c, self.slope), self.w[f"{n}.deconv.weight"], self.w.get(f"{n}.deconv.bias"),
-                self.state[n], s)
+                c, self.w[f"{n}.deconv.weight"], self.w.get(f"{n}.deconv.bias"),
+                c[:, :, :1] if self.offline else self.state[n], s)
             if grp == 1 and len(self.p["resblock_kernel_sizes"]) > 1:
                 # AD v0: MultiReceptiveField.inference (multi_fusion.py:73-79) over HiFiGANResidualBlock.inference
                 # (residual_block.py:100-105)
@@ -269,6 +293,15 @@ class HiFiGANOracle:
             c = F.conv1d(x, self.w[f"blocks.{i}.conv_out.weight"], None)   # :140
         c = self._conv("output_conv", F.leaky_relu(c, 0.01))   # :294-296 (nn.LeakyReLU() default slope, :116)
         return torch.tanh(c)
+
+    def forward(self, c):                                # HiFiGAN.py:140-160 Generator.forward; c (B,in_channels,F) channels-first
+        self.reset_buffer()
+        self.offline = True
+        try:
+            return self.decode(c.transpose(2, 1))
+        finally:
+            self.offline = False
+            self.reset_buffer()
 
 
 # --------------------------------------------------------------------------- end-to-end helper

@@ -183,3 +183,33 @@ def test_bitstream_oracle_known_answer_and_round_trip():
     # hand-computed vector: local indices 1..8, 10 bits each
     idx = (np.arange(8) + 1 + 1024 * np.arange(8)).reshape(8, 1, 1)
     assert BO.pack_indices(idx, 1024).ravel().tolist() == [1, 8, 48, 0, 1, 5, 24, 112, 0, 2]
+
+
+OFFLINE = {   # golden file -> (encoder params, vocoder params or None)
+    "offline_symad.npz": ("SYMAD_PARAMS", None), "offline_aad.npz": ("SYMAAD_PARAMS", None),
+    "offline_c16.npz": ("SYMAD_C16_PARAMS", None), "offline_v1.npz": ("SYMAD_PARAMS", "HIFIGAN_V1_PARAMS"),
+    "offline_v0.npz": ("SYMAD_PARAMS", "HIFIGAN_V0_PARAMS"),
+}
+
+
+@pytest.mark.parametrize("fname", sorted(OFFLINE))
+def test_offline_forward_oracle_vs_reference(golden_dir, fname):
+    """the non-streaming batch forward of codecTest.py:78-95 (zero left-pad, replication pad on the
+    transposed convs), oracle restatement vs vectors dumped from the reference's base Generator classes."""
+    g = np.load(os.path.join(golden_dir, fname))
+    ep, vp = (getattr(S, n) if n else None for n in OFFLINE[fname])
+    enc = O.SymADOracle(ep, S.symad_state_dict(ep, seed=0))
+    x = torch.from_numpy(g["x"])
+    with torch.no_grad():
+        z = enc.forward_encode(x)
+        zq = enc.forward_quantize(z)
+        if vp is None:
+            y = O.SymADOracle(ep, S.symad_state_dict(ep, seed=0)).forward_decode(zq)
+        else:
+            y = O.HiFiGANOracle(vp, S.hifigan_state_dict(vp, seed=1)).forward(zq)
+    # fp32 conv summation order depends on the host thread count (goldens: 4 threads), hence not bit-exact
+    np.testing.assert_allclose(z.numpy(), g["z"], atol=5e-6)
+    np.testing.assert_allclose(zq.numpy(), g["zq"], atol=5e-6)
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=1e-5)
+    # and the streaming state of the oracle object is untouched (zeros) afterwards
+    assert all(float(v.abs().max()) == 0.0 for v in enc.state.values())

@@ -284,3 +284,50 @@ def test_index_bitstream_16_codebooks():
     assert tuple(p.shape) == (2, 9, 20)
     np.testing.assert_array_equal(p.cpu().numpy(), BO.pack_indices(idx, 1024))
     np.testing.assert_array_equal(g.unpack(p).cpu().numpy(), idx)
+
+
+OFFLINE = {   # golden file -> (encoder params, vocoder params or None)
+    "offline_symad.npz": ("SYMAD_PARAMS", None), "offline_aad.npz": ("SYMAAD_PARAMS", None),
+    "offline_c16.npz": ("SYMAD_C16_PARAMS", None), "offline_v1.npz": ("SYMAD_PARAMS", "HIFIGAN_V1_PARAMS"),
+    "offline_v0.npz": ("SYMAD_PARAMS", "HIFIGAN_V0_PARAMS"),
+}
+
+
+@pytest.mark.parametrize("fname", sorted(OFFLINE))
+def test_offline_forward_golden(golden_dir, fname, conv_path):
+    """the non-streaming batch forward (codecTest.py:78-95) against vectors dumped from the reference's base
+    Generator classes: zero left-pad on every causal conv, first-frame replication on every transposed conv."""
+    from audiodec_b200.codec import HiFiGANStreamGenerator, OfflineCodec, SymADStreamGenerator
+    g = np.load(os.path.join(golden_dir, fname))
+    ep, vp = (getattr(S, n) if n else None for n in OFFLINE[fname])
+    dev = torch.device("cuda:0")
+    enc = SymADStreamGenerator(**ep)
+    enc.load_state_dict(S.symad_state_dict(ep, seed=0))
+    enc = enc.eval().to(dev)
+    if vp is None:
+        dec = SymADStreamGenerator(**ep)
+        dec.load_state_dict(S.symad_state_dict(ep, seed=0))
+    else:
+        dec = HiFiGANStreamGenerator(**vp)
+        dec.load_state_dict(S.hifigan_state_dict(vp, seed=1))
+    dec = dec.eval().to(dev)
+    x = torch.from_numpy(g["x"]).cuda()
+    # a streaming call first: the offline forward must not depend on whatever state the handle holds
+    enc.initial_encoder(8192, dev)
+    z = enc.encode_offline(x)
+    zq, idx = enc.quantize_offline(z)
+    y = dec.forward(zq) if vp is not None else dec.decode_offline(zq)
+    torch.cuda.synchronize()
+    assert tuple(z.shape) == tuple(g["z"].shape) and tuple(zq.shape) == tuple(g["zq"].shape) and tuple(y.shape) == tuple(g["y"].shape)
+    np.testing.assert_allclose(z.cpu().numpy(), g["z"], atol=Z_TOL)
+    np.testing.assert_allclose(zq.cpu().numpy(), g["zq"], atol=5e-6)        # sum of codewords vs sum of x+(e-x) roundings
+    np.testing.assert_allclose(y.cpu().numpy(), g["y"], atol=WAVE_TOL)
+    # same through the codecTest.py-shaped wrapper ((T,C) audio in), and a different batch size on the same handles
+    oc = OfflineCodec(enc, dec)
+    audio = g["x"][:, 0, :].T                                              # (T, C=B)
+    y2 = oc.decode(oc.encode(audio))
+    np.testing.assert_array_equal(y2.cpu().numpy(), y.cpu().numpy())
+    y1 = oc.decode(oc.encode(audio[:, :1]))
+    np.testing.assert_allclose(y1.cpu().numpy(), g["y"][:1], atol=WAVE_TOL)
+    y3 = oc.decode(oc.encode(np.concatenate([audio, audio[:, :1]], axis=1)))
+    np.testing.assert_allclose(y3.cpu().numpy()[-1], g["y"][0], atol=WAVE_TOL)

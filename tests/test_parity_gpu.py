@@ -331,3 +331,37 @@ def test_offline_forward_golden(golden_dir, fname, conv_path):
     np.testing.assert_allclose(y1.cpu().numpy(), g["y"][:1], atol=WAVE_TOL)
     y3 = oc.decode(oc.encode(np.concatenate([audio, audio[:, :1]], axis=1)))
     np.testing.assert_allclose(y3.cpu().numpy()[-1], g["y"][0], atol=WAVE_TOL)
+
+
+def test_multi_stream_server_matches_per_stream_oracle(symad_sd):
+    """three lock-stepped streams through the batched server (indices over the packed wire format) equal
+    three independent reference-style streams, including a stream that under-runs one step (it is fed silence)."""
+    from audiodec_b200.server import MultiStreamCodecServer
+    from oracle import audiodec_oracle as O
+    tx, rx, dec, _ = _codec(symad_sd)
+    n, fs, steps = 3, 1500, 3
+    srv = MultiStreamCodecServer(tx, rx, dec, n_streams=n, frame_size=fs, sample_rate=48000, max_latency=1.0,
+                                 device="cuda:0", wire=True)
+    torch.manual_seed(5)
+    frames = 0.1 * torch.randn(steps, n, fs)
+    skip = (1, 2)                                                  # stream 2 has nothing queued at step 1
+    for k in range(steps):
+        for s in range(n):
+            if (k, s) != skip:
+                srv.submit(s, frames[k, s].numpy())
+        assert srv.step() == (n - 1 if k == skip[0] else n)
+    for s in range(n):
+        orc = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
+        for k in range(steps):
+            x = torch.zeros(1, 1, fs) if (k, s) == skip else frames[k, s].view(1, 1, fs)
+            y = orc.run(x)[-1]
+            if (k, s) == skip:
+                continue
+            out = srv.poll(s)
+            assert out is not None and out.shape == (fs,)
+            np.testing.assert_allclose(out, y.numpy().reshape(-1)[:fs], atol=WAVE_TOL)
+        assert srv.poll(s) is None
+    st = srv.statistics()
+    assert st["frames"] == steps * n - 1 and st["underruns"] == 1 and st["frame_drops"] == 0
+    assert st["wire_kbps_per_stream"] == pytest.approx(12.8)       # 8 x 10 bit per 300-sample frame at 48 kHz
+    assert not tx.index_error() and not rx.index_error()

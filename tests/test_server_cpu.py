@@ -1,0 +1,145 @@
+"""Host logic of the multi-stream server (audiodec_b200/server.py) on duck-typed stand-in codecs:
+lock-step batching, per-stream causal state, underrun fill, late-stream drop policy (bin/stream.py:262-270 per stream),
+latency accounting, the real-time tick thread.  No GPU, no CUDA extension."""
+import time
+
+import numpy as np
+import pytest
+import torch
+
+from audiodec_b200.server import MultiStreamCodecServer
+
+
+class FakeCodec:
+    """Stateful stand-in with the reference's duck-typed surface: y[t] = 2 * (x[t] + last sample of the previous frame).
+    State is per stream and is replicated from the single warmed stream on the first batched call, like the real handles."""
+
+    def __init__(self):
+        self.carry = torch.zeros(1, 1, 1)
+        self.calls = 0
+
+    def encode(self, x):
+        if self.carry.shape[0] != x.shape[0]:
+            assert self.carry.shape[0] == 1
+            self.carry = self.carry.repeat(x.shape[0], 1, 1)
+        z = x + self.carry
+        self.carry = x[:, :, -1:].clone()
+        self.calls += 1
+        return z
+
+    def quantize(self, z):
+        return z
+
+    def lookup(self, idx):
+        return idx
+
+    def decode(self, zq):
+        return 2.0 * zq
+
+    def pack(self, idx):
+        return idx.contiguous().view(torch.uint8)
+
+    def unpack(self, packed):
+        return packed.view(torch.float32)
+
+
+class FakeClock:
+    def __init__(self):
+        self.t = 100.0
+
+    def __call__(self):
+        self.t += 0.001
+        return self.t
+
+
+def _server(n, **kw):
+    c = FakeCodec()
+    kw.setdefault("frame_size", 8)
+    kw.setdefault("sample_rate", 8000)
+    return MultiStreamCodecServer(c, c, c, n_streams=n, **kw), c
+
+
+def test_lockstep_batches_keep_per_stream_state():
+    srv, codec = _server(3, max_latency=1.0, clock=FakeClock())
+    rng = np.random.default_rng(0)
+    frames = rng.standard_normal((4, 3, 8)).astype(np.float32)          # (step, stream, sample)
+    for k in range(4):
+        for s in range(3):
+            srv.submit(s, frames[k, s])
+        assert srv.step() == 3
+    assert codec.calls == 4                                              # ONE codec call per step for all streams
+    for s in range(3):
+        prev = 0.0
+        for k in range(4):
+            out = srv.poll(s)
+            np.testing.assert_allclose(out, 2.0 * (frames[k, s] + prev), rtol=0, atol=1e-6)
+            prev = frames[k, s, -1]
+        assert srv.poll(s) is None
+    st = srv.statistics()
+    assert st["frames"] == 12 and st["frame_drops"] == 0 and st["underruns"] == 0 and st["steps"] == 4
+    assert all(p["latency_ms"][0] > 0 for p in st["per_stream"])
+
+
+def test_underrun_is_fed_silence_and_produces_no_output():
+    srv, _ = _server(2, max_latency=1.0)
+    a = np.arange(8, dtype=np.float32)
+    srv.submit(0, a), srv.submit(1, a)
+    srv.step()
+    srv.submit(0, a)                               # stream 1 misses this step
+    assert srv.step() == 1
+    srv.submit(0, a), srv.submit(1, a)
+    srv.step()
+    outs0 = [srv.poll(0) for _ in range(3)]
+    outs1 = [srv.poll(1) for _ in range(3)]
+    assert all(o is not None for o in outs0) and outs1[2] is None and srv.stats[1].underruns == 1
+    np.testing.assert_allclose(outs0[2], 2.0 * (a + a[-1]))
+    np.testing.assert_allclose(outs1[1], 2.0 * (a + 0.0))     # its state saw the silent frame, not the frame before it
+    assert srv.stats[1].n_frames == 2 and srv.stats[0].n_frames == 3
+
+
+def test_late_stream_drops_oldest_frames():
+    srv, _ = _server(1, frame_size=8, sample_rate=8000, max_latency=0.002)     # 0.002 s * 8000 / 8 = 2 frames of backlog
+    assert srv.max_backlog == 2
+    fr = [np.full(8, i, np.float32) for i in range(5)]
+    for f in fr:
+        srv.submit(0, f)
+    assert srv.pending(0) == 2 and srv.stats[0].frame_drops == 3
+    srv.step(), srv.step()
+    np.testing.assert_allclose(srv.poll(0), 2.0 * fr[3])                       # the two newest survive, in order
+    np.testing.assert_allclose(srv.poll(0), 2.0 * (fr[4] + 3.0))
+    assert srv.statistics()["frame_drops"] == 3
+
+
+def test_bad_arguments_raise():
+    srv, _ = _server(2)
+    with pytest.raises(ValueError):
+        srv.submit(0, np.zeros(7, np.float32))
+    with pytest.raises(IndexError):
+        srv.submit(5, np.zeros(8, np.float32))
+    with pytest.raises(ValueError):
+        MultiStreamCodecServer(None, None, None, n_streams=0)
+
+
+def test_wire_mode_counts_packed_bytes():
+    srv, _ = _server(2, wire=True, max_latency=1.0)
+    for _ in range(3):
+        srv.submit(0, np.ones(8, np.float32)), srv.submit(1, np.ones(8, np.float32))
+        srv.step()
+    st = srv.statistics()
+    assert srv.wire_bytes == 3 * 2 * 8 * 4 and st["wire_kbps_per_stream"] == pytest.approx(8e-3 * 96 / (3 * 8 / 8000))
+    assert srv.poll(0) is not None
+
+
+def test_realtime_tick_thread_drains_queues():
+    srv, _ = _server(2, max_latency=10.0)
+    for k in range(5):
+        srv.submit(0, np.full(8, k, np.float32)), srv.submit(1, np.full(8, -k, np.float32))
+    srv.start(period=0.002)
+    deadline = time.time() + 5.0
+    while (srv.pending(0) or srv.pending(1)) and time.time() < deadline:
+        time.sleep(0.005)
+    srv.stop()
+    assert srv.pending(0) == 0 and srv.pending(1) == 0
+    got = [srv.poll(0) for _ in range(5)]
+    assert all(g is not None for g in got) and float(got[4][0]) == 2.0 * (4 + 3)
+    assert srv.statistics()["frames"] == 10

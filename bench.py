@@ -221,9 +221,10 @@ def run_ours(args):
                 print(f"  {k:44s} {v[1] / v[0]:8.3f} ms  {v[2] / (v[1] / v[0]) / 1e6:8.1f} GB/s(alg)", file=sys.stderr)
             print(f"  sum of launches per step: {tot / 2:.3f} ms", file=sys.stderr)
         dname, (dn, dms, dbytes) = top[0]
-        prof = {"kernel": dname, "launch_ms": dms / dn, "alg_bytes_per_launch": dbytes, "share_of_step": dms / tot,
-                "conv_kernels_share_of_step": sum(v[1] for k, v in agg.items() if "res_units" in k or ".conv" in k or "project" in k
-                                                  or "blocks" in k or "upsamples" in k) / tot,
+        step_ms = ms_total / args.steps                 # shares are of the TIMED step (which also holds the RVQ / lookup launches)
+        prof = {"kernel": dname, "launch_ms": dms / dn, "alg_bytes_per_launch": dbytes, "share_of_step": (dms / dn) / step_ms,
+                "conv_kernels_share_of_step": sum(v[1] / 2 for k, v in agg.items() if "res_units" in k or ".conv" in k or "project" in k
+                                                  or "blocks" in k or "upsamples" in k) / step_ms,
                 "top5": [{"op": k, "ms": v[1] / v[0], "GBps": v[2] / (v[1] / v[0]) / 1e6} for k, v in top[:5]]}
 
     if world > 1:

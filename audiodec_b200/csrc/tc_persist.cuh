@@ -21,13 +21,9 @@
 namespace adec {
 
 template <int NT> struct TcpCfg {
-#ifdef ADEC_ALT_NT64
-    static constexpr int MB = 1;
-    static constexpr int STAGES = NT == 64 ? 6 : TcCfg<NT>::STAGES;
-#else
-    static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128)
+    static constexpr int MB = NT == 64 ? 2 : 1;            // fused-intermediate smem buffers (smem permitting; 2 stages + 2 buffers measured slower at NT=128,
+                                                           // 6 stages + 1 buffer slower at NT=64)
     static constexpr int STAGES = TcCfg<NT>::STAGES;       // weight stages (at NT=32: 4 stages measured 13 % SLOWER than 3, 8 no faster)
-#endif
     // MMA issuer warps take groups c = 0,1,2,... round robin.  Every mbarrier must have waiters that see each of its phases in
     // order (a parity wait cannot tell phase k from phase k-2), so a weight stage (c % STAGES) and a TMEM partial (c % NPB) must
     // always belong to the same warp: NW divides both.  Odd ring depth -> three issuer warps.

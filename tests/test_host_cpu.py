@@ -201,3 +201,31 @@ def test_bench_cuda_arm_fails_loudly_without_a_gpu():
                          capture_output=True, text=True, env=dict(os.environ, CUDA_VISIBLE_DEVICES=""), timeout=600)
     assert out.returncode != 0
     assert not [l for l in out.stdout.splitlines() if l.startswith("{")]
+
+
+def test_wav_io_pcm16_round_trip(tmp_path):
+    """audiodec_b200/wavio.py: demoFile.py's sf.read(always_2d) / sf.write(PCM_16) conventions."""
+    import numpy as np
+    from audiodec_b200.wavio import read_wav, write_wav_pcm16
+    p = str(tmp_path / "a.wav")
+    x = np.stack([np.array([0.0, 0.5, -1.0, 1.0, 0.25], np.float32), np.array([0.1, -0.1, 0.0, 0.9, -0.9], np.float32)], axis=1)
+    write_wav_pcm16(p, x, 48000)
+    y, fs = read_wav(p)
+    assert fs == 48000 and y.shape == (5, 2) and y.dtype == np.float32
+    np.testing.assert_allclose(y, x, atol=5e-5)         # 32767 on write, 32768 on read, half an LSB of rounding
+    from scipy.io import wavfile
+    raw = wavfile.read(p)[1]
+    assert raw.dtype == np.int16 and raw[:, 0].tolist() == [0, 16384, -32767, 32767, 8192]
+    write_wav_pcm16(p, x[:, 0], 24000)                     # mono (T,) is written and read back as (T, 1)
+    y1, fs1 = read_wav(p)
+    assert fs1 == 24000 and y1.shape == (5, 1)
+
+
+def test_demo_file_cli_refuses_cpu_and_missing_input(tmp_path):
+    from audiodec_b200 import demo_file
+    with pytest.raises(SystemExit):
+        demo_file.main(["--model", "vctk_v1", "-i", "x.wav", "-o", "y.wav", "--cuda", "-1"])
+    with pytest.raises(NotImplementedError):
+        demo_file.main(["--model", "no_such_model", "-i", "x.wav", "-o", "y.wav"])
+    with pytest.raises(ValueError):
+        demo_file.main(["--model", "vctk_v1", "-i", str(tmp_path / "missing.wav"), "-o", "y.wav"])

@@ -213,3 +213,35 @@ def test_offline_forward_oracle_vs_reference(golden_dir, fname):
     np.testing.assert_allclose(y.numpy(), g["y"], atol=1e-5)
     # and the streaming state of the oracle object is untouched (zeros) afterwards
     assert all(float(v.abs().max()) == 0.0 for v in enc.state.values())
+
+
+def test_bitstream_and_shard_properties_hypothesis():
+    """Size-independent properties: unpack(pack(idx)) == idx for any codebook count / size, frames are independent
+    (packing a batch == packing its frames one by one), and shard bounds always tile [0, n) contiguously and evenly."""
+    from hypothesis import given, settings, strategies as st
+    from audiodec_b200.shard import shard_bounds
+    from oracle import bitstream_oracle as BO
+
+    @settings(max_examples=40, deadline=None)
+    @given(nq=st.integers(1, 16), n=st.integers(2, 4096), b=st.integers(1, 3), f=st.integers(1, 5), seed=st.integers(0, 2**31 - 1))
+    def bitstream(nq, n, b, f, seed):
+        rng = np.random.default_rng(seed)
+        idx = rng.integers(0, n, (nq, b, f)) + n * np.arange(nq)[:, None, None]
+        p = BO.pack_indices(idx, n)
+        assert p.shape == (b, f, BO.frame_bytes(nq, n)) and p.dtype == np.uint8
+        np.testing.assert_array_equal(BO.unpack_indices(p, nq, n), idx)
+        np.testing.assert_array_equal(p[b - 1, f - 1], BO.pack_indices(idx[:, b - 1:, f - 1:], n)[0, 0])
+        pad_bits = 8 * BO.frame_bytes(nq, n) - nq * BO.index_bits(n)
+        assert 0 <= pad_bits < 8 and int(p[0, 0, -1]) >> (8 - pad_bits) == 0 if pad_bits else True
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(0, 5000), w=st.integers(1, 16))
+    def shards(n, w):
+        bnd = shard_bounds(n, w)
+        sizes = [e - s for s, e in bnd]
+        assert len(bnd) == w and bnd[0][0] == 0 and bnd[-1][1] == n and sum(sizes) == n
+        assert all(bnd[i][1] == bnd[i + 1][0] for i in range(w - 1)) and max(sizes) - min(sizes) <= 1
+        assert sizes == sorted(sizes, reverse=True)
+
+    bitstream()
+    shards()

@@ -143,3 +143,54 @@ def test_realtime_tick_thread_drains_queues():
     got = [srv.poll(0) for _ in range(5)]
     assert all(g is not None for g in got) and float(got[4][0]) == 2.0 * (4 + 3)
     assert srv.statistics()["frames"] == 10
+
+
+def test_server_over_the_oracle_codec_equals_independent_streams():
+    """The same scenario as the GPU test (tests/test_parity_gpu.py::test_multi_stream_server_matches_per_stream_oracle), with the
+    torch-CPU oracle standing in for the CUDA handles: three lock-stepped streams (one under-runs a step) through the server,
+    indices over the packed wire format, against three independent batch-1 streams."""
+    from audiodec_b200 import synthetic as S
+    from oracle import audiodec_oracle as O
+    from oracle import bitstream_oracle as BO
+
+    class Wire:                               # adds the pack / unpack surface of SymADStreamGenerator to an oracle object
+        def __init__(self, orc):
+            self.o = orc
+
+        def __getattr__(self, name):
+            return getattr(self.o, name)
+
+        def pack(self, idx):
+            return torch.from_numpy(BO.pack_indices(idx.numpy(), 1024))
+
+        def unpack(self, packed):
+            return torch.from_numpy(BO.unpack_indices(packed.numpy(), 8, 1024))
+
+    sd = S.symad_state_dict(seed=0)
+    codec = O.CodecOracle(S.SYMAD_PARAMS, sd)
+    n, fs, steps = 3, 1500, 3
+    srv = MultiStreamCodecServer(Wire(codec.tx_encoder), Wire(codec.rx_encoder), codec.decoder, n_streams=n, frame_size=fs,
+                                 sample_rate=48000, max_latency=1.0, wire=True)
+    torch.manual_seed(5)
+    frames = 0.1 * torch.randn(steps, n, fs)
+    skip = (1, 2)
+    for k in range(steps):
+        for s in range(n):
+            if (k, s) != skip:
+                srv.submit(s, frames[k, s].numpy())
+        assert srv.step() == (n - 1 if k == skip[0] else n)
+    for s in range(n):
+        orc = O.CodecOracle(S.SYMAD_PARAMS, sd)
+        for k in range(steps):
+            x = torch.zeros(1, 1, fs) if (k, s) == skip else frames[k, s].view(1, 1, fs)
+            with torch.no_grad():
+                y = orc.run(x)[-1]
+            if (k, s) == skip:
+                continue
+            out = srv.poll(s)
+            assert out is not None and out.shape == (fs,)
+            np.testing.assert_allclose(out, y.numpy().reshape(-1)[:fs], atol=1e-5)
+        assert srv.poll(s) is None
+    st = srv.statistics()
+    assert st["frames"] == steps * n - 1 and st["underruns"] == 1 and st["frame_drops"] == 0
+    assert st["wire_kbps_per_stream"] == pytest.approx(12.8)

@@ -27,30 +27,33 @@ def run_file(audiodec, data: np.ndarray) -> np.ndarray:
     return y.squeeze(1).transpose(1, 0).cpu().numpy()
 
 
+def _arguments(argv):
+    """Same flags as the reference demo (demoFile.py:21-27)."""
+    ap = argparse.ArgumentParser(description="wav -> AudioDec codec on a B200 -> wav")
+    ap.add_argument("--model", default="libritts_v1", help="name from assign_model's table")
+    ap.add_argument("-i", "--input", required=True, help="input wav (sample rate must match the model)")
+    ap.add_argument("-o", "--output", required=True, help="output wav, written as PCM_16")
+    ap.add_argument("--cuda", type=int, default=0, help="CUDA ordinal; negative (the reference's CPU mode) is refused")
+    ap.add_argument("--num_threads", type=int, default=4, help="host threads for torch (only plumbing runs there)")
+    return ap.parse_args(argv)
+
+
 def main(argv=None):
-    parser = argparse.ArgumentParser()
-    parser.add_argument("--model", type=str, default="libritts_v1")
-    parser.add_argument("-i", "--input", type=str, required=True)
-    parser.add_argument("-o", "--output", type=str, required=True)
-    parser.add_argument("--cuda", type=int, default=0)
-    parser.add_argument("--num_threads", type=int, default=4)
-    args = parser.parse_args(argv)
-    if args.cuda < 0:
+    opt = _arguments(argv)
+    if opt.cuda < 0:
         raise SystemExit("audiodec_b200 has no CPU path: pass --cuda <ordinal>")
-    device = f"cuda:{args.cuda}"
-    torch.set_num_threads(args.num_threads)
-    sample_rate, encoder_checkpoint, decoder_checkpoint = assign_model(args.model)
-    if not os.path.exists(args.input):
-        raise ValueError(f"Input file {args.input} does not exist!")
-    print("AudioDec initinalizing!")
-    audiodec = AudioDec(tx_device=device, rx_device=device)
-    audiodec.load_transmitter(encoder_checkpoint)
-    audiodec.load_receiver(encoder_checkpoint, decoder_checkpoint)
-    data, fs = read_wav(args.input)
-    assert fs == sample_rate, f"data ({fs}Hz) is not matched to model ({sample_rate}Hz)!"
-    print("Encode/Decode...")
-    write_wav_pcm16(args.output, run_file(audiodec, data), fs)
-    print(f"Output {args.output}!")
+    torch.set_num_threads(opt.num_threads)
+    rate, enc_ckpt, dec_ckpt = assign_model(opt.model)          # NotImplementedError for an unknown name, like the reference
+    if not os.path.exists(opt.input):
+        raise ValueError(f"Input file {opt.input} does not exist!")
+    dev = f"cuda:{opt.cuda}"
+    codec = AudioDec(tx_device=dev, rx_device=dev)
+    codec.load_transmitter(enc_ckpt)
+    codec.load_receiver(enc_ckpt, dec_ckpt)
+    audio, fs = read_wav(opt.input)
+    assert fs == rate, f"data ({fs}Hz) is not matched to model ({rate}Hz)!"
+    write_wav_pcm16(opt.output, run_file(codec, audio), fs)
+    print(f"wrote {opt.output}: {audio.shape[0] / fs:.2f} s, {audio.shape[1]} channel(s)")
 
 
 if __name__ == "__main__":

@@ -194,3 +194,36 @@ def test_server_over_the_oracle_codec_equals_independent_streams():
     st = srv.statistics()
     assert st["frames"] == steps * n - 1 and st["underruns"] == 1 and st["frame_drops"] == 0
     assert st["wire_kbps_per_stream"] == pytest.approx(12.8)
+
+
+def test_single_stream_streamer_pipeline_with_stand_in_codec():
+    """AudioDecStreamer (utils/audiodec.py:65-106 over bin/stream.py:80-278): frames go callback -> encoder thread -> decoder
+    thread -> callback in order; zeros are played until the pipeline has filled; nothing is dropped under the latency budget."""
+    from audiodec_b200.utils.audiodec import AudioDecStreamer
+
+    class Stateless:
+        def encode(self, x):
+            return x
+
+        def quantize(self, z):
+            return z
+
+        def lookup(self, idx):
+            return idx
+
+        def decode(self, zq):
+            return 2.0 * zq
+
+    c = Stateless()
+    s = AudioDecStreamer(input_device=0, output_device=0, frame_size=8, sample_rate=2000, max_latency=5.0,
+                         tx_encoder=c, tx_device="cpu", rx_encoder=c, decoder=c, rx_device="cpu")
+    frames = [np.full((8, 1), k + 1, np.float32) for k in range(30)]
+    outs = s.process_frames(frames, realtime=True)                 # 4 ms per frame
+    assert len(outs) == 30 and all(o.shape == (8, 1) for o in outs)
+    vals = [float(o[0, 0]) for o in outs]
+    played = [v for v in vals if v != 0.0]
+    assert len(played) >= 20                                       # the two worker threads keep up with a 4 ms period
+    assert played == [2.0 * (k + 1) for k in range(len(played))]   # in order, nothing skipped, gain applied by decode
+    assert vals[:len(vals) - len(played)] == [0.0] * (len(vals) - len(played))
+    st = s.statistics()
+    assert st["n_frames"] == 30 and st["frame_drops"] == 0 and st["latency_ms"][0] < 5000

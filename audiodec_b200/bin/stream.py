@@ -180,6 +180,18 @@ class AudioCodecStreamer(abc.ABC):
         print("system latency (ms):               %.2f +- %.2f" % s["latency_ms"])
         print("frame drops:                       %d (%.2f%%)" % (self.frame_drops, 100.0 * self.frame_drops / max(1, self.n_frames)))
         print("#" * 80)
+        self._write_dumps()
+
+    def _write_dumps(self):
+        # bin/stream.py:285-293: concatenate the frames seen by the callback, clamp to [-1, 1], write PCM16 wavs
+        from ..wavio import write_wav_pcm16
+        for name, frames in ((self.input_dump_filename, self.input_dump), (self.output_dump_filename, self.output_dump)):
+            if name is None or not frames:
+                continue
+            wav = torch.clamp(torch.cat(frames, dim=-1), -1.0, 1.0)           # (channels, n_samples)
+            write_wav_pcm16(name, wav.transpose(1, 0).numpy(), self.sample_rate)
+            print("Wrote %s (%d samples)" % (name, wav.shape[-1]))
+        self.input_dump, self.output_dump = [], []
 
     def enable_filedump(self, input_stream_file: str = None, output_stream_file: str = None):
         if input_stream_file is None and output_stream_file is None:

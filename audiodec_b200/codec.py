@@ -103,6 +103,12 @@ class _StreamGeneratorBase:
             raise RuntimeError(f"input is on {t.device}, codec is on {self._device}")
         return t.to(dtype).contiguous()
 
+    @staticmethod
+    def _want(t, what, dim, size):
+        """torch raises RuntimeError on a wrong feature dimension; the C ABI takes no D argument, so check here."""
+        if t.dim() != 3 or t.size(dim) != size:
+            raise RuntimeError(f"audiodec_b200: {what}: expected a 3-D tensor with size {size} in dim {dim}, got {tuple(t.shape)}")
+
     def _batch(self, b):
         n = self._lib.adec_n_streams(self._h)
         if n != b:
@@ -197,6 +203,7 @@ class SymADStreamGenerator(_StreamGeneratorBase):
     def quantize(self, z):
         """z (B,code_dim,F) -> idx int64 (Nq,F) for B==1 else (Nq,B,F)   (AudioDec.py:237-239)"""
         self._ready()
+        self._want(z, "quantize", 1, self.code_dim)
         z = self._in(z)
         b, _, f = z.shape
         idx = torch.empty(self.codebook_num, b, f, device=self._device, dtype=torch.int64)
@@ -209,6 +216,8 @@ class SymADStreamGenerator(_StreamGeneratorBase):
         idx = self._in(idx, torch.int64)
         if idx.dim() == 2:
             idx = idx.unsqueeze(1)
+        if idx.dim() != 3 or idx.size(0) != self.codebook_num:
+            raise RuntimeError(f"audiodec_b200: lookup: expected ({self.codebook_num},F) or ({self.codebook_num},B,F) indices, got {tuple(idx.shape)}")
         _, b, f = idx.shape
         zq = torch.empty(b, f, self.code_dim, device=self._device, dtype=torch.float32)
         _check(self._lib.adec_lookup(self._h, _ptr(idx), b, f, _ptr(zq), self._stream()), self._h)
@@ -218,6 +227,10 @@ class SymADStreamGenerator(_StreamGeneratorBase):
     def encode_offline(self, x):
         """x (B,1,T) -> z (B,code_dim,F): Encoder.forward + Projector.forward, zero left-pad (conv_layer.py:148-151)."""
         self._ready()
+        if x.dim() != 3:
+            raise RuntimeError("encode_offline expects (batch, channel, length)")
+        if x.size(1) != self.input_channels:                 # same fold as encode(): every audio channel is its own batch row
+            x = x.reshape(-1, self.input_channels, x.size(-1))
         x = self._in(x)
         b, _, t = x.shape
         f = self._lib.adec_frames_for(self._h, t)
@@ -228,6 +241,7 @@ class SymADStreamGenerator(_StreamGeneratorBase):
     def quantize_offline(self, z):
         """z (B,code_dim,F) -> (zq (B,code_dim,F) channels-first like Quantizer.forward (quantizer.py:31-34), idx (Nq,B,F))."""
         self._ready()
+        self._want(z, "quantize_offline", 1, self.code_dim)
         z = self._in(z)
         b, _, f = z.shape
         idx = torch.empty(self.codebook_num, b, f, device=self._device, dtype=torch.int64)
@@ -285,6 +299,7 @@ class SymADStreamGenerator(_StreamGeneratorBase):
     def decode(self, zq):
         """zq (B,F,D) channels-last -> y (B,1,F*hop)   (AudioDec.py:246-247)"""
         self._ready()
+        self._want(zq, "decode", 2, self.code_dim)
         zq = self._in(zq)
         b, f, _ = zq.shape
         self._batch(b)
@@ -295,6 +310,7 @@ class SymADStreamGenerator(_StreamGeneratorBase):
 
 def _decode_offline(gen, zq):
     gen._ready()
+    gen._want(zq, "decode_offline / forward", 1, getattr(gen, "code_dim", None) or gen.in_channels)
     zq = gen._in(zq)
     b, _, f = zq.shape
     zq_cl = zq.transpose(1, 2).contiguous()                       # the kernels' native channels-last (B,F,D)
@@ -344,6 +360,7 @@ class HiFiGANStreamGenerator(_StreamGeneratorBase):
     def decode(self, c):
         """zq (B,F,in_channels) channels-last -> y (B,1,F*prod(scales)) in (-1,1)   (HiFiGAN.py:268-296)"""
         self._ready()
+        self._want(c, "decode", 2, self.in_channels)
         c = self._in(c)
         b, f, _ = c.shape
         self._batch(b)
@@ -365,6 +382,9 @@ class OfflineCodec:
     CUDA device; they must not be the handles a live stream is using (offline calls reset the causal state)."""
 
     def __init__(self, encoder, decoder, multi_channel=False):
+        if multi_channel and encoder.input_channels == 1:
+            # codecTest.py:84-86 feeds (1,C,T) to a multi-channel generator; a mono generator would silently encode channel 0 only
+            raise NotImplementedError("multi_channel=True needs a generator with input_channels > 1 (only mono generators are built)")
         self.encoder, self.decoder, self.multi_channel = encoder, decoder, multi_channel
 
     def encode(self, audio):

@@ -36,6 +36,7 @@ class AdecConfig(ctypes.Structure):
         ("has_stats", c_int),
         ("codec_activate", c_int),
         ("n_resblocks", c_int), ("resblock_kernel_sizes", _I8),
+        ("compute_dtype", c_int),
     ]
 
 
@@ -64,7 +65,9 @@ SYMBOLS = {
     "adec_pack_indices": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "adec_unpack_indices": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "adec_index_error": (c_int, [c_void_p, c_void_p]),
+    "adec_range_error": (c_int, [c_void_p, c_void_p]),
     "adec_launch_count": (c_int64, [c_void_p]),
+    "adec_probe_mma": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "adec_profile": (c_int, [c_void_p, c_int]),
     "adec_profile_report": (c_int, [c_void_p, c_char_p, c_int]),
     "adec_test_causal_conv": (c_int, [c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,

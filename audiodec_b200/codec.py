@@ -59,6 +59,8 @@ class _StreamGeneratorBase:
         return self
 
     def to(self, device):
+        if isinstance(device, torch.dtype):
+            return self._set_dtype(device)
         device = torch.device(device)
         if device.type != "cuda":
             raise RuntimeError("audiodec_b200 runs on CUDA (sm_100a) only; there is no CPU fallback")
@@ -81,6 +83,26 @@ class _StreamGeneratorBase:
         _check(self._lib.adec_finalize(h), h)
         self._sd = None
         return self
+
+    def _set_dtype(self, dtype):
+        """`module.to(torch.bfloat16)` of the reference: only the HiFi-GAN vocoder has a reduced-precision mode (bf16 conv operands,
+        fp32 accumulation and fp32 activations in HBM); the encoder / projector / RVQ must stay fp32-grade for bit-identical indices."""
+        if dtype == torch.float32:
+            want = 0
+        elif dtype == torch.bfloat16 and self._cfg.model_type == _lib.MODEL_HIFIGAN:
+            want = 1
+        else:
+            raise NotImplementedError(f"{type(self).__name__} has no {dtype} mode (fp32 everywhere; bf16 for the HiFi-GAN vocoder only)")
+        if self._h is not None and want != self._cfg.compute_dtype:
+            raise RuntimeError("set the compute dtype before .to(device): the weights are packed when the handle is created")
+        self._cfg.compute_dtype = want
+        return self
+
+    def bfloat16(self):
+        return self._set_dtype(torch.bfloat16)
+
+    def float(self):
+        return self._set_dtype(torch.float32)
 
     def __del__(self):
         try:
@@ -138,6 +160,14 @@ class _StreamGeneratorBase:
             name, ms, nbytes = line.split("\t")
             rows.append((name, float(ms), float(nbytes)))
         return rows
+
+    def range_error(self):
+        """True if an activation left the fp16-split range of the default conv engine since the last call (synchronises)."""
+        self._ready()
+        rc = self._lib.adec_range_error(self._h, self._stream())
+        if rc < 0:
+            raise RuntimeError("audiodec_b200: " + _lib.last_error(self._h))
+        return bool(rc)
 
     def reset_buffer(self):
         """AudioDec.py:250-256 / HiFiGAN.py:298-305."""

@@ -21,6 +21,10 @@
 #include "kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_persist.cuh"
+#include "tc_f16.cuh"
+#include "probe.cuh"
+#include <cuda_fp16.h>
+#include <cuda_bf16.h>
 
 using namespace adec;
 
@@ -92,38 +96,7 @@ const ConvKernelCfg* find_conv_kernel(int CW, int CO, bool fuse) {
     return nullptr;
 }
 
-// tensor-core (tcgen05, 3xTF32) instantiations: NT = output-channel tile (UMMA N)
-template <int NT, bool F, int PRE>
-cudaError_t launch_tc(const ConvArgs& a, dim3 grid, int smem_bytes, cudaStream_t s) {
-    static bool configured[64] = {false};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    auto kern = tc_conv_kernel<NT, F, PRE>;
-#ifdef ADEC_TIMELINE
-    constexpr int kMaxDyn = 227 * 1024 - 2048;   // room for the static timeline buffer
-#else
-    constexpr int kMaxDyn = 227 * 1024;
-#endif
-    if (dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-        if (e != cudaSuccess) return e;
-        configured[dev] = true;
-    }
-    if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
-    constexpr int CL = TcCfg<NT>::CLUSTER;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((grid.x + CL - 1) / CL * CL, grid.y, grid.z);     // padded tiles are fully masked in the kernel
-    cfg.blockDim = dim3(TcCfg<NT>::THREADS);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, a);
-}
-
+// tensor-core (tcgen05, 3xTF32; ADEC_CONV_PATH=tf32) instantiations: NT = output-channel tile (UMMA N)
 inline int TcpCfgStages(int NT) { return NT == 128 ? TcpCfg<128>::STAGES : NT == 64 ? TcpCfg<64>::STAGES : TcpCfg<32>::STAGES; }
 // persistent variant: one CTA per SM loops over (time tile, channel tile, stream) tiles
 typedef cudaError_t (*TcPersistFn)(const ConvArgs&, int, int, int, int, int, cudaStream_t);
@@ -148,8 +121,8 @@ cudaError_t launch_tcp(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tile
     return cudaGetLastError();
 }
 
-struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; ConvLaunchFn fn; TcPersistFn pfn; };
-#define ADEC_TC1(NT, F, PRE) {NT, TC_CP, TcCfg<NT>::STAGES, F, PRE, launch_tc<NT, F, PRE>, launch_tcp<NT, F, PRE>}
+struct TcKernelCfg { int NT, KS, stages; bool fuse; int pre; TcPersistFn pfn; };
+#define ADEC_TC1(NT, F, PRE) {NT, TC_CP, TcCfg<NT>::STAGES, F, PRE, launch_tcp<NT, F, PRE>}
 #define ADEC_TC(NT) \
     ADEC_TC1(NT, true, ACT_ELU), ADEC_TC1(NT, false, ACT_NONE), ADEC_TC1(NT, false, ACT_ELU), ADEC_TC1(NT, false, ACT_LRELU), \
     ADEC_TC1(NT, false, ACT_NORM)
@@ -161,6 +134,44 @@ const TcKernelCfg* find_tc_kernel(int NT, bool fuse, int pre) {
         if (k.NT == NT && k.fuse == fuse && k.pre == pre) return &k;
     return nullptr;
 }
+
+// tcgen05 kind::f16 engine (tc_f16.cuh; default): PREC 3 = two fp16 pieces per operand, three products (fp32-grade);
+// PREC 1 = bf16 operands, one product (the vocoder's bf16 mode)
+template <int NT, bool F, int PRE, int PREC>
+cudaError_t launch_tcf(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tiles, int n_ctas, int smem_bytes, cudaStream_t s) {
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    auto kern = tc_conv_f16_kernel<NT, F, PRE, PREC>;
+    constexpr int kMaxDyn = 227 * 1024;
+    if (dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
+    kern<<<n_ctas, TcfCfg<NT, PREC>::THREADS, smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
+    return cudaGetLastError();
+}
+typedef size_t (*TcfSmemFn)(int, bool);
+typedef int (*TcfWbufFn)(int, bool);
+struct TcfKernelCfg { int NT; bool fuse; int pre, prec, tap_bytes; TcPersistFn pfn; TcfSmemFn smem; TcfWbufFn n_wbuf; };
+#define ADEC_TCF1(NT, F, PRE, PREC) \
+    {NT, F, PRE, PREC, TcfCfg<NT, PREC>::TAP_BYTES, launch_tcf<NT, F, PRE, PREC>, TcfCfg<NT, PREC>::smem_bytes, TcfCfg<NT, PREC>::n_wbuf}
+#define ADEC_TCF(NT) \
+    ADEC_TCF1(NT, true, ACT_ELU, 3), ADEC_TCF1(NT, false, ACT_NONE, 3), ADEC_TCF1(NT, false, ACT_ELU, 3), ADEC_TCF1(NT, false, ACT_LRELU, 3), \
+    ADEC_TCF1(NT, false, ACT_NORM, 3), ADEC_TCF1(NT, false, ACT_NONE, 1), ADEC_TCF1(NT, false, ACT_LRELU, 1), ADEC_TCF1(NT, false, ACT_NORM, 1)
+const TcfKernelCfg kTcfKernels[] = {ADEC_TCF(128), ADEC_TCF(64), ADEC_TCF(32)};
+
+const TcfKernelCfg* find_tcf_kernel(int NT, bool fuse, int pre, int prec) {
+    for (const auto& k : kTcfKernels)
+        if (k.NT == NT && k.fuse == fuse && k.pre == pre && k.prec == prec) return &k;
+    return nullptr;
+}
+
+uint16_t half_bits(float x) { const __half h = __float2half_rn(x); uint16_t u; memcpy(&u, &h, 2); return u; }
+float half_value(uint16_t u) { __half h; memcpy(&h, &u, 2); return __half2float(h); }
+uint16_t bf16_bits(float x) { const __nv_bfloat16 h = __float2bfloat16_rn(x); uint16_t u; memcpy(&u, &h, 2); return u; }
 
 float tf32_round_host(float x) {   // cvt.rna.tf32.f32: round to nearest (ties away), 10-bit mantissa
     uint32_t u;
@@ -196,7 +207,9 @@ struct Op {
     std::vector<float> hstate;  // initial state (P, st_C) or empty (zeros)
     // kernel config
     const ConvKernelCfg* kc = nullptr;
-    const TcKernelCfg* tc = nullptr;   // tensor-core path (default); kc = FFMA path
+    const TcKernelCfg* tc = nullptr;   // 3xTF32 tensor-core path; kc = FFMA path
+    const TcfKernelCfg* tcf = nullptr; // kind::f16 tensor-core path (default)
+    float w_scale = 1.f, w2_scale = 1.f;
     int n_pieces = 1, n_co_tiles = 1;
     // device
     float *w = nullptr, *w2 = nullptr, *bias = nullptr;
@@ -228,8 +241,9 @@ struct adec_handle {
     std::vector<Op> enc_ops, dec_ops;
     int n_streams = 1;
     int st_cap = 1;        // streams the state buffers were allocated for
-    bool use_tc = true;           // ADEC_CONV_PATH=ffma selects the CUDA-core kernels
-    int persist_mask = 32 | 64 | 128;  // ADEC_TC_PERSIST: bit mask of channel-tile widths (32|64|128) that use the persistent kernel
+    int engine = 2;               // ADEC_CONV_PATH: 2 = f16 (tcgen05 kind::f16, default), 1 = tf32 (round-1 3xTF32), 0 = ffma (CUDA cores)
+    bool use_tc = true;           // any tensor-core engine
+    bool bf16 = false;            // cfg.compute_dtype == 1: bf16 operands (HiFi-GAN vocoder, f16 engine only)
     int n_sms = 148;
     DevBuf ws[3];
     std::vector<void*> owned;     // device allocations freed in destroy
@@ -434,7 +448,7 @@ int finalize_op_tc(adec_handle* h, Op* op) {
     int NT = op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
     // 96 outputs (transposed conv 64 -> 3*32): one zero-padded 128-wide tile beats three 32-wide tiles that each rebuild the
     // same activation window and are smem-operand bound (persistent kernel only: its epilogue masks per 32-column piece)
-    const bool pad_tile = !op->fuse && NT == 32 && op->Cout > 64 && op->Cout < 128 && (h->persist_mask & 128);
+    const bool pad_tile = !op->fuse && NT == 32 && op->Cout > 64 && op->Cout < 128;
     if (pad_tile) NT = 128;
     op->tc = find_tc_kernel(NT, op->fuse, op->pre_act);
     if (!op->tc || (op->fuse && (NT != op->Cout || op->mid_act != op->pre_act))) return h->fail(op->name + ": no tensor-core kernel");
@@ -479,8 +493,81 @@ int finalize_op_tc(adec_handle* h, Op* op) {
     return 0;
 }
 
+// kind::f16 engine: weights as fp16 (hi | lo | hi * 2^-11) of w * 2^p, or one bf16 plane, in UMMA K-major no-swizzle blocks:
+//   [group g][co tile][piece][tap][plane][kb = 8-channel block][NT rows][8 x 16 bit]
+// one (piece, tap) = TAP_BYTES; the kernel's weight producer copies one or two consecutive taps per stage (tc_f16.cuh).
+int finalize_op_f16(adec_handle* h, Op* op) {
+    int NT = op->Cout % 128 == 0 ? 128 : op->Cout % 64 == 0 ? 64 : 32;
+    const bool pad_tile = !op->fuse && NT == 32 && op->Cout > 64 && op->Cout < 128;     // e.g. transposed conv 64 -> 3*32: one padded 128-wide tile
+    if (pad_tile) NT = 128;
+    const int prec = (h->bf16 && !op->fuse) ? 1 : 3;
+    op->tcf = find_tcf_kernel(NT, op->fuse, op->pre_act, prec);
+    if (!op->tcf || (op->fuse && (NT != op->Cout || op->mid_act != op->pre_act))) return h->fail(op->name + ": no tensor-core kernel");
+    const int CP = TC_CP, KB = F16_KB, npl = prec == 3 ? 3 : 1;
+    op->n_pieces = op->Cin_eff / CP;
+    op->n_co_tiles = pad_tile ? 1 : op->Cout / NT;
+    const size_t tap_bytes = (size_t)op->tcf->tap_bytes;
+    op->w_tile_floats = (long long)((size_t)op->n_pieces * op->Ktaps * tap_bytes / 4);
+    auto pow2_scale = [](const std::vector<float>& w, int* p_out) {
+        float wmax = 0.f;
+        for (float v : w) wmax = std::max(wmax, std::fabs(v));
+        int p = 0;
+        if (wmax > 0.f && std::isfinite(wmax)) {
+            while (std::ldexp(wmax, p) < 4096.f) ++p;
+            while (std::ldexp(wmax, p) >= 8192.f) --p;
+        }
+        *p_out = p;
+    };
+    auto pack = [&](const float* weff, int G, int ntiles, int pieces, int taps, int cin_eff, int cout, int p2, std::vector<float>* out) {
+        std::vector<uint16_t> img((size_t)G * ntiles * pieces * taps * tap_bytes / 2, 0);
+        size_t o = 0;     // in 16-bit units
+        for (int g = 0; g < G; ++g)
+            for (int nt = 0; nt < ntiles; ++nt)
+                for (int pc = 0; pc < pieces; ++pc)
+                    for (int tap = 0; tap < taps; ++tap) {
+                        for (int kb = 0; kb < KB; ++kb)
+                            for (int n = 0; n < NT; ++n)
+                                for (int e = 0; e < 8; ++e) {
+                                    const int k = pc * CP + kb * 8 + e;
+                                    const float w = nt * NT + n < cout ? weff[(((size_t)g * taps + tap) * cin_eff + k) * cout + nt * NT + n] : 0.f;
+                                    const size_t at = o + ((size_t)kb * NT + n) * 8 + e, plane = (size_t)KB * NT * 8;
+                                    if (prec == 3) {
+                                        const float ws = std::ldexp(w, p2);
+                                        const uint16_t hi = half_bits(ws);
+                                        img[at] = hi;
+                                        img[at + plane] = half_bits(ws - half_value(hi));
+                                        img[at + 2 * plane] = half_bits(half_value(hi) * (1.0f / 2048.0f));
+                                    } else {
+                                        img[at] = bf16_bits(w);
+                                    }
+                                }
+                        o += (size_t)npl * KB * NT * 8;
+                    }
+        out->assign((img.size() + 1) / 2, 0.f);
+        memcpy(out->data(), img.data(), img.size() * 2);
+    };
+    int p1 = 0, p2 = 0;
+    if (prec == 3) pow2_scale(op->weff, &p1);
+    op->w_scale = std::ldexp(1.0f, -p1);
+    std::vector<float> packed;
+    pack(op->weff.data(), op->G, op->n_co_tiles, op->n_pieces, op->Ktaps, op->Cin_eff, op->Cout, p1, &packed);
+    if (dev_upload(h, &op->w, packed)) return 1;
+    if (op->fuse) {
+        pow2_scale(op->weff2, &p2);
+        op->w2_scale = std::ldexp(1.0f, -p2);
+        std::vector<float> pk2;
+        pack(op->weff2.data(), 1, 1, op->Cout / CP, 1, op->Cout, op->Cout, p2, &pk2);
+        if (dev_upload(h, &op->w2, pk2)) return 1;
+    }
+    if (!op->hbias.empty() && dev_upload(h, &op->bias, op->hbias)) return 1;
+    std::vector<float>().swap(op->weff);
+    std::vector<float>().swap(op->weff2);
+    return 0;
+}
+
 int finalize_op(adec_handle* h, Op* op) {
     if (op->kind != OP_CONV) return 0;
+    if (h->engine == 2) return finalize_op_f16(h, op);
     if (h->use_tc) return finalize_op_tc(h, op);
     int CW, CO;
     if (op->fuse) {
@@ -521,7 +608,7 @@ int alloc_state(adec_handle* h, Op* op, int n_streams) {
     const size_t per = (size_t)op->P * op->st_C;
     if (per == 0) return 0;
     for (int i = 0; i < 2; ++i) {
-        if (dev_alloc(h, &op->st[i], per * n_streams)) return 1;
+        CK(h, cudaMalloc((void**)&op->st[i], per * n_streams * sizeof(float)));     // owned by the op: freed on resize / destroy
         CK(h, cudaMemset(op->st[i], 0, per * n_streams * sizeof(float)));
     }
     op->cur = 0;
@@ -532,7 +619,10 @@ int alloc_state(adec_handle* h, Op* op, int n_streams) {
     return 0;
 }
 
-// pad_buffer (1, C, P) from the state dict -> (P, st_C) channels-last initial state
+// pad_buffer (1, C, P) from the state dict -> (P, st_C) channels-last initial state.  The reference stores in pad_buffer the tail of
+// what it feeds to conv.inference, i.e. values AFTER the pre-activation / normalisation (residual_unit.py:79 `conv1.inference(
+// self.activation(x))`, HiFiGAN.py:276-284,288), and the kernels keep exactly that: state rows are never activated again (only chunk
+// rows are, while the window is written), so checkpoint values are copied as they are.
 void load_pad_buffer(adec_handle* h, Op* op, const std::string& key, int c_real) {
     const HostTensor* pb = find(h, key);
     if (!pb || pb->shape.size() != 3 || op->P == 0) return;
@@ -617,23 +707,25 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.y_bs = op.out_nct ? (long long)op.G * op.Cout * Tout : (long long)Tout * op.ldy;
             a.mid_act = op.mid_act;
             a.hist_rep = (rc.offline && op.up > 1) ? 1 : 0;
-            if (op.tc) {
+            a.w_scale = op.w_scale; a.w2_scale = op.w2_scale; a.err = h->d_err;
+            if (op.tcf || op.tc) {
+                // persistent tensor-core kernels: one CTA per SM loops over (time tile, channel tile, stream) tiles
                 const int wrows = TC_TT + (op.Ktaps - 1) * op.dil;
-                const int wrp = std::max(wrows, 129) | 1;
-                const int buf1_rows = op.n_pieces > 1 ? wrp : (op.fuse ? 129 : 0);
-                const size_t smem = 256 + sizeof(float) * ((size_t)op.tc->stages * 2 * op.tc->KS * op.tc->NT +
-                                                           (size_t)2 * TC_CP * (wrp + buf1_rows));
+                const int NT = op.tcf ? op.tcf->NT : op.tc->NT;
                 dim3 grid((Tout + TC_TT - 1) / TC_TT, op.G * op.n_co_tiles, rc.B);
-                if (h->persist_mask & op.tc->NT) {
-                    const int pst = TcpCfgStages(op.tc->NT), pmb = op.tc->NT == 128 ? TcpCfg<128>::MB : op.tc->NT == 64 ? TcpCfg<64>::MB : TcpCfg<32>::MB;
-                    const size_t psmem = 512 + sizeof(float) * ((size_t)pst * 2 * op.tc->KS * op.tc->NT + (size_t)4 * TC_CP * wrp +
-                                                                (op.fuse ? (size_t)pmb * 2 * TC_CP * TC_MIDP : 0));
-                    const long long n_tiles = (long long)grid.x * grid.y * grid.z;
-                    const int n_ctas = (int)std::min<long long>(n_tiles, h->n_sms);
-                    e = op.tc->pfn(a, (int)grid.x, (int)grid.y, (int)n_tiles, n_ctas, (int)psmem, rc.stream);
+                const long long n_tiles = (long long)grid.x * grid.y * grid.z;
+                const int n_ctas = (int)std::min<long long>(n_tiles, h->n_sms);
+                size_t psmem;
+                if (op.tcf) {
+                    psmem = op.tcf->smem(wrows, op.fuse);
+                    a.n_wbuf = op.tcf->n_wbuf(wrows, op.fuse);
+                    if (a.n_wbuf < 2) return h->fail(fmt("%s: window of %d rows does not fit in shared memory", op.name.c_str(), wrows));
                 } else {
-                    e = op.tc->fn(a, grid, (int)smem, rc.stream);
+                    const int wrp = std::max(wrows, 129) | 1;
+                    const int pst = TcpCfgStages(NT), pmb = NT == 128 ? TcpCfg<128>::MB : NT == 64 ? TcpCfg<64>::MB : TcpCfg<32>::MB;
+                    psmem = 512 + sizeof(float) * ((size_t)pst * 2 * op.tc->KS * NT + (size_t)4 * TC_CP * wrp + (op.fuse ? (size_t)pmb * 2 * TC_CP * TC_MIDP : 0));
                 }
+                e = (op.tcf ? op.tcf->pfn : op.tc->pfn)(a, (int)grid.x, (int)grid.y, (int)n_tiles, n_ctas, (int)psmem, rc.stream);
             } else {
                 const int TT = op.kc->TT;
                 dim3 grid((Tout + TT - 1) / TT, op.G * op.n_co_tiles, rc.B);
@@ -1026,8 +1118,21 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     auto* h = new adec_handle();
     h->cfg = *cfg;
     h->device = device;
-    if (const char* pth = getenv("ADEC_CONV_PATH")) h->use_tc = strcmp(pth, "ffma") != 0;
-    if (const char* pm = getenv("ADEC_TC_PERSIST")) h->persist_mask = atoi(pm);
+    if (const char* pth = getenv("ADEC_CONV_PATH")) {
+        if (!strcmp(pth, "ffma")) h->engine = 0;
+        else if (!strcmp(pth, "tf32")) h->engine = 1;
+        else if (!strcmp(pth, "f16") || !strcmp(pth, "tc") || !*pth) h->engine = 2;
+        else { g_create_error = std::string("ADEC_CONV_PATH must be f16, tf32 or ffma, not ") + pth; delete h; return 1; }
+    }
+    h->use_tc = h->engine != 0;
+    h->bf16 = cfg->compute_dtype == 1;
+    if (cfg->compute_dtype != 0 && cfg->compute_dtype != 1) { g_create_error = "compute_dtype must be 0 (fp32) or 1 (bf16)"; delete h; return 1; }
+    if (h->bf16 && (cfg->model_type != ADEC_MODEL_HIFIGAN || h->engine != 2)) {
+        g_create_error = "compute_dtype = bf16 is built for the HiFi-GAN vocoder on the f16 tensor-core engine only (the encoder, projector and RVQ "
+                         "must stay fp32-grade for bit-identical indices)";
+        delete h;
+        return 1;
+    }
     if (const char* mf = getenv("ADEC_TC_MAXFUSE")) kTcMaxFuse = atoi(mf);
     cudaDeviceGetAttribute(&h->n_sms, cudaDevAttrMultiProcessorCount, device);
     DeviceGuard dg(device);
@@ -1044,6 +1149,9 @@ void adec_destroy(adec_handle* h) {
     if (!h) return;
     DeviceGuard dg(h->device);
     for (void* p : h->owned) cudaFree(p);
+    for (auto* ops : {&h->enc_ops, &h->dec_ops})
+        for (Op& op : *ops)
+            for (int i = 0; i < 2; ++i) if (op.st[i]) cudaFree(op.st[i]);
     for (auto& b : h->ws) if (b.p) cudaFree(b.p);
     for (DevBuf* b : {&h->hx, &h->hz, &h->hzq, &h->hy}) if (b->p) cudaFree(b->p);
     if (h->hidx) cudaFree(h->hidx);
@@ -1086,49 +1194,52 @@ int adec_finalize(adec_handle* h) {
 
 int adec_n_streams(const adec_handle* h) { return h ? h->n_streams : 0; }
 
-int adec_set_streams(adec_handle* h, int n) {
-    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
-    if (n == h->n_streams) return 0;
-    if (n < 1) return h->fail("n_streams must be >= 1");
-    if (h->n_streams != 1) return h->fail(fmt("can only expand from 1 stream (have %d); reset or re-create", h->n_streams));
-    DeviceGuard dg(h->device);
+// Resize the per-stream causal state to n streams.  Streams that exist keep their state; new streams either copy stream 0
+// (replicate: the "warm one stream, then fan out" case) or start from zero history (= reset_buffer() on them).  Buffers grow on
+// demand and the replaced ones are freed.
+static int resize_state(adec_handle* h, int n, bool replicate) {
+    const int keep = std::min(n, h->n_streams);
     CK(h, cudaDeviceSynchronize());
     for (auto* ops : {&h->enc_ops, &h->dec_ops})
         for (Op& op : *ops) {
             const size_t per = (size_t)op.P * op.st_C;
             if (!per) continue;
-            float* nb[2];
-            for (int i = 0; i < 2; ++i) {
-                if (dev_alloc(h, &nb[i], per * n)) return 1;
+            if (n > h->st_cap) {
+                float* nb[2] = {nullptr, nullptr};
+                for (int i = 0; i < 2; ++i) CK(h, cudaMalloc((void**)&nb[i], per * n * sizeof(float)));
+                CK(h, cudaMemcpy(nb[0], op.st[op.cur], per * keep * sizeof(float), cudaMemcpyDeviceToDevice));
+                for (int i = 0; i < 2; ++i) cudaFree(op.st[i]);
+                op.st[0] = nb[0]; op.st[1] = nb[1]; op.cur = 0;
             }
-            const long long tot = (long long)per * n;
-            replicate_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(nb[0], op.st[op.cur], (long long)per, n);
-            CK(h, cudaGetLastError());
-            CK(h, cudaMemset(nb[1], 0, per * n * sizeof(float)));
-            op.st[0] = nb[0]; op.st[1] = nb[1]; op.cur = 0;   // old buffers stay in `owned` until destroy
+            if (n > keep) {
+                float* tail = op.st[op.cur] + per * keep;
+                const long long tot = (long long)per * (n - keep);
+                if (replicate) {
+                    replicate_kernel<<<(unsigned)((tot + 255) / 256), 256>>>(tail, op.st[op.cur], (long long)per, n - keep);
+                    CK(h, cudaGetLastError());
+                } else {
+                    CK(h, cudaMemset(tail, 0, tot * sizeof(float)));
+                }
+            }
         }
     CK(h, cudaDeviceSynchronize());
+    h->st_cap = std::max(h->st_cap, n);
     h->n_streams = n;
-    h->st_cap = n;
     return 0;
+}
+
+int adec_set_streams(adec_handle* h, int n) {
+    if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
+    if (n == h->n_streams) return 0;
+    if (n < 1) return h->fail("n_streams must be >= 1");
+    DeviceGuard dg(h->device);
+    return resize_state(h, n, /*replicate=*/h->n_streams == 1);
 }
 
 // Non-streaming forward (codecTest.py:78-95): any batch size, every causal conv starts from a zero left-pad
 // (conv_layer.py:148-151) = zeroed state for exactly B streams.  Discards the handle's streaming state.
 static int offline_state(adec_handle* h, int B, cudaStream_t s) {
-    if (B > h->st_cap) {
-        CK(h, cudaDeviceSynchronize());
-        for (auto* ops : {&h->enc_ops, &h->dec_ops})
-            for (Op& op : *ops) {
-                const size_t per = (size_t)op.P * op.st_C;
-                if (!per) continue;
-                for (int i = 0; i < 2; ++i)
-                    if (dev_alloc(h, &op.st[i], per * B)) return 1;     // old buffers stay in `owned` until destroy
-                op.cur = 0;
-            }
-        h->st_cap = B;
-    }
-    h->n_streams = B;
+    if (B != h->n_streams && resize_state(h, B, false)) return 1;
     return adec_reset(h, (void*)s);
 }
 
@@ -1244,9 +1355,14 @@ int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int
     if (idx_host) CK(enc, cudaMemcpyAsync(idx_host, enc->hidx, nidx * sizeof(long long), cudaMemcpyDeviceToHost, s));
     CK(enc, cudaMemcpyAsync(y_host, enc->hy.p, (size_t)B * F * hop * sizeof(float), cudaMemcpyDeviceToHost, s));
     CK(enc, cudaStreamSynchronize(s));
-    int herr = 0;
-    CK(enc, cudaMemcpy(&herr, enc->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-    if (herr) return enc->fail("lookup: index out of range");
+    for (adec_handle* hh : {enc, dec}) {
+        int herr = 0;
+        CK(enc, cudaMemcpy(&herr, hh->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (herr) CK(enc, cudaMemset(hh->d_err, 0, sizeof(int)));
+        if (herr & 1) return enc->fail("lookup: index out of range");
+        if (herr & 2) return enc->fail("an activation left the range of the fp16-split tensor-core engine (|a| >= 6e4); use ADEC_CONV_PATH=tf32");
+        if (hh == dec) break;     // enc == dec
+    }
     return 0;
 }
 
@@ -1282,20 +1398,56 @@ int adec_unpack_indices(adec_handle* h, const uint8_t* packed, int B, int F, int
     return pack_common(h, "unpack_indices", idx, B, F, const_cast<uint8_t*>(packed), stream, false);
 }
 
-int adec_index_error(adec_handle* h, void* stream) {
+// device flag word: bit 0 = out-of-range index (lookup / pack / unpack), bit 1 = activation outside the fp16-split range
+static int read_flag(adec_handle* h, void* stream, int bit) {
     if (!h || !h->d_err) return -1;
     DeviceGuard dg(h->device);
     int herr = 0;
     if (cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess ||
-        cudaMemcpy(&herr, h->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess ||
-        cudaMemset(h->d_err, 0, sizeof(int)) != cudaSuccess) {
-        h->fail("index_error: CUDA error while reading the flag");
+        cudaMemcpy(&herr, h->d_err, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) {
+        h->fail("CUDA error while reading the device flag word");
         return -1;
     }
-    return herr;
+    if (herr & bit) {
+        const int rest = herr & ~bit;
+        if (cudaMemcpy(h->d_err, &rest, sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) { h->fail("CUDA error while clearing the device flag word"); return -1; }
+    }
+    return (herr & bit) ? 1 : 0;
 }
 
+int adec_index_error(adec_handle* h, void* stream) { return read_flag(h, stream, 1); }
+int adec_range_error(adec_handle* h, void* stream) { return read_flag(h, stream, 2); }
+
 int64_t adec_launch_count(const adec_handle* h) { return h ? h->launches : 0; }
+
+int adec_probe_mma(int device, int kind, int NT, int n_groups, double* tflops, double* ms) {
+    if (!tflops || (kind != 0 && kind != 1) || NT < 16 || NT > 256 || NT % 16 || n_groups < 1) { g_create_error = "probe_mma: bad argument"; return 1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_create_error = "probe_mma: no usable CUDA device"; return 1; }
+    DeviceGuard dg(device);
+    int n_sms = 0;
+    cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
+    const int smem = 8 * 2 * (128 + NT) * 16;
+    auto launch = [&](cudaStream_t s) {
+        if (kind == 0) { cudaFuncSetAttribute(mma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); mma_probe_kernel<0><<<n_sms, 128, smem, s>>>(NT, n_groups); }
+        else { cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); mma_probe_kernel<1><<<n_sms, 128, smem, s>>>(NT, n_groups); }
+    };
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    launch(0);                                   // warm-up: clocks, instruction cache
+    cudaEventRecord(e0, 0);
+    launch(0);
+    cudaEventRecord(e1, 0);
+    cudaError_t e = cudaEventSynchronize(e1);
+    float t = 0.f;
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&t, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_create_error = fmt("probe_mma: %s", cudaGetErrorString(e)); return 1; }
+    const double flops = (double)n_sms * n_groups * 12.0 * 2.0 * 128.0 * NT * (kind == 0 ? 8.0 : 16.0);
+    *tflops = flops / (t * 1e-3) / 1e12;
+    if (ms) *ms = t;
+    return 0;
+}
 
 int adec_profile(adec_handle* h, int enable) {
     if (!h) return 1;

@@ -55,13 +55,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* b, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU.  The clock is only consulted every
-// 64 failed probes so the common path stays a 2-instruction loop.
+// 64 failed probes so the common path stays a 2-instruction loop.  The bound is ~20 s of SM clocks: far beyond any legitimate wait
+// even when the context is time-sliced with other tenants (clock64 keeps counting while descheduled); -DADEC_NO_WATCHDOG compiles
+// the check out (plain try_wait loop with the hardware suspend hint).
+#ifndef ADEC_WATCHDOG_CYCLES
+#define ADEC_WATCHDOG_CYCLES 40000000000LL
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag = 0) {
     if (mbar_try_wait(b, parity)) return;
+#ifdef ADEC_NO_WATCHDOG
+    while (!mbar_try_wait(b, parity)) { }
+    return;
+#endif
     const long long t0 = clock64();
     for (unsigned it = 1;; ++it) {
         if (mbar_try_wait(b, parity)) return;
-        if ((it & 63u) == 0 && clock64() - t0 > 4000000000LL) {
+        if ((it & 63u) == 0 && clock64() - t0 > ADEC_WATCHDOG_CYCLES) {
             printf("adec: mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x);
             __trap();
@@ -138,6 +147,10 @@ struct ConvArgs {
     int mid_act;         // FUSE: activation between the two GEMMs
     int hist_rep;        // non-streaming forward of a transposed conv: history rows = the FIRST input row (ReplicationPad1d,
                          // conv_layer.py:189-192) instead of the stored state
+    // tcgen05 kind::f16 engine (tc_f16.cuh): weights are stored times a power of two; the drain warps multiply the sums by these
+    float w_scale, w2_scale;
+    int n_wbuf;          // window buffers in shared memory (2..4)
+    int* err;            // device flag word: bit 1 = an activation left the fp16-split range (|a| >= 6e4)
 };
 
 constexpr int CONV_STAGES = 4;
@@ -438,41 +451,56 @@ struct HeadArgs {
     float* y; long long y_bs;
 };
 
+// Eight lanes share one run of R = 8 consecutive outputs: lane c4 owns channels 4*c4..4*c4+3, loads the R + K - 1 window rows of its
+// channel quad straight from global (a row is one coalesced 128-byte segment across the eight lanes; no shared memory, every input row
+// is read 14/8 times from L1), applies the pre-activation in registers and accumulates its 4-channel share of the R dot products with
+// the K x 4 weights it keeps in registers; three xor-shuffles add the eight shares and lane j stores output j.  The layer moves
+// 128 B per output row and does 2*K*CIN flops on it: memory-bound once the LDS traffic of the round-1 version (112 LDS.128 per output)
+// is gone.
 template <int CIN, int K>
 __global__ void __launch_bounds__(256) head_kernel(const HeadArgs a) {
-    constexpr int TT = 256, P = K - 1, PITCH = CIN + 4;
-    __shared__ __align__(16) float xs[(TT + P) * PITCH];
-    __shared__ __align__(16) float sw[K * CIN];
-    const int b = blockIdx.y, j0 = blockIdx.x * TT, tid = threadIdx.x;
+    static_assert(CIN == 32, "eight lanes x four channels");
+    constexpr int R = 8, P = K - 1, TT = 256;
+    const int b = blockIdx.y, tid = threadIdx.x, c4 = tid & 7;
+    const int t0 = blockIdx.x * TT + (tid >> 3) * R;               // first output of this lane group
     const float* xg = a.x + (long long)b * a.x_bs;
     const float* sg = a.st_in + (long long)b * P * CIN;
-    for (int idx = tid; idx < (TT + P) * (CIN / 4); idx += 256) {
-        const int m = idx / (CIN / 4), ci = (idx - m * (CIN / 4)) * 4;
-        const long long i = (long long)j0 + m;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < P) v = *reinterpret_cast<const float4*>(sg + i * CIN + ci);
-        else if (i - P < a.T) v = apply_act(__ldg(reinterpret_cast<const float4*>(xg + (i - P) * a.ldx + ci)), a.pre_act, a.slope);
-        *reinterpret_cast<float4*>(xs + m * PITCH + ci) = v;
-    }
-    for (int i = tid; i < K * CIN; i += 256) sw[i] = a.w[i];
-    __syncthreads();
-    const int t = tid;
-    if (j0 + t < a.T) {
-        float acc = 0.f;
+    float4 w[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            const float* xr = xs + (t + k) * PITCH;
+    for (int k = 0; k < K; ++k) w[k] = __ldg(reinterpret_cast<const float4*>(a.w + k * CIN) + c4);
+    float acc[R];
 #pragma unroll
-            for (int ci = 0; ci < CIN; ci += 4) {
-                const float4 xv = *reinterpret_cast<const float4*>(xr + ci);
-                const float4 wv = *reinterpret_cast<const float4*>(sw + k * CIN + ci);
-                acc = fmaf(xv.x, wv.x, acc); acc = fmaf(xv.y, wv.y, acc);
-                acc = fmaf(xv.z, wv.z, acc); acc = fmaf(xv.w, wv.w, acc);
-            }
+    for (int j = 0; j < R; ++j) acc[j] = 0.f;
+    if (t0 < a.T) {
+        float4 xv[R + P];
+#pragma unroll
+        for (int r = 0; r < R + P; ++r) {
+            const long long i = (long long)t0 + r;                  // x~ row = history(P) || chunk
+            xv[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < P) xv[r] = __ldg(reinterpret_cast<const float4*>(sg + i * CIN) + c4);            // state rows are stored post-activation
+            else if (i - P < a.T) xv[r] = apply_act(__ldg(reinterpret_cast<const float4*>(xg + (i - P) * a.ldx) + c4), a.pre_act, a.slope);
         }
-        acc += a.bias;
-        if (a.post_tanh) acc = tanhf(acc);
-        a.y[(long long)b * a.y_bs + j0 + t] = acc;
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                acc[j] = fmaf(xv[j + k].x, w[k].x, acc[j]); acc[j] = fmaf(xv[j + k].y, w[k].y, acc[j]);
+                acc[j] = fmaf(xv[j + k].z, w[k].z, acc[j]); acc[j] = fmaf(xv[j + k].w, w[k].w, acc[j]);
+            }
+    }
+    float mine = 0.f;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        float v = acc[j];
+        v += __shfl_xor_sync(0xffffffffu, v, 1);
+        v += __shfl_xor_sync(0xffffffffu, v, 2);
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        if (j == c4) mine = v;
+    }
+    if (t0 + c4 < a.T) {
+        mine += a.bias;
+        if (a.post_tanh) mine = tanhf(mine);
+        a.y[(long long)b * a.y_bs + t0 + c4] = mine;
     }
     if (blockIdx.x == gridDim.x - 1) {
         float* so = a.st_out + (long long)b * P * CIN;

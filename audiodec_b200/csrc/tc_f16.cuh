@@ -1,0 +1,545 @@
+// tc_conv_f16_kernel: the causal conv family on tcgen05 `kind::f16` tensor cores, persistent, sm_100a (round 2 default engine).
+//
+// Same ConvArgs contract and the same schedule as the round-1 3xTF32 kernel (tc_persist.cuh): GEMM orientation M = 128 time
+// steps (TMEM lanes), N = output-channel tile NT (TMEM columns), K = input channels of one tap; both operands K-major,
+// no-swizzle "column blocks"  smem[(kb * ROWS + row) * 16 B]  (kb = 16-byte block of 8 channels, SBO = 128 B, LBO = ROWS*16 B),
+// so a conv tap is a row-shifted start address of the same window - no im2col, no copies.  What changed is the arithmetic:
+//
+//   PREC = 3 (fp32-grade, every layer that must stay within 1e-4 / bit-identical indices)
+//       a     = A_hi + 2^-11 A_lo         A_hi = fp16(a),      A_lo = fp16((a - A_hi) * 2^11)        (producer warps)
+//       w * s = W_hi + W_lo               W_hi = fp16(w * s),  W_lo = fp16(w * s - W_hi),  W_his = 2^-11 W_hi   (host, s = 2^p per op:
+//                                                                                            max|w| s in [2^12, 2^13) keeps all three normal)
+//       a w s ~= A_lo W_his + A_hi W_lo + A_hi W_hi     three fp16 products, fp32 accumulation in TMEM, result * 2^-p in the drain warps.
+//     fp16 and tf32 both carry 11 significand bits, so this is as accurate as 3xTF32 (dropped term ~2^-22 relative; measured in
+//     tools/tc_probe3.cu: max error 6.5e-7 of the output rms at K = 224, below a plain fp32 FMA chain's 1.8e-6) - but one fp16 MMA
+//     covers K = 16 where a tf32 MMA covers K = 8 for the same issue slot and the same shared-memory operand bytes: half the
+//     tensor-pipe time and half the operand reads per conv.  Range: |a| < 65504 (checked in the epilogue, ConvArgs::err).
+//   PREC = 1 (bf16 operands, one product; the HiFi-GAN vocoder's bf16 mode, BASELINE configs[2])
+//
+// The TMEM accumulator still truncates at every accumulation step (tools/tc_probe2.cu, tc_probe3.cu: -2e-7 of the rms over 14 chained
+// steps), so accumulation stays GROUPED: one group = one 32-channel piece x TWO taps = 4 full-magnitude MMAs (preceded by the 8
+// small-term MMAs) into a fresh TMEM partial; drain warps add the partials into fp32 registers with round-to-nearest adds
+// (bias -6.7e-8 of the rms).  Groups are twice as long as in round 1 (K = 64), so the drain work per conv halves too.
+//
+// Warp roles, barriers and the barrier rule are those of tc_persist.cuh: warp 0 = weight producer (1-D TMA bulk
+// copies of host-packed stages) + TMEM allocator, warps 1..NW = MMA issuers taking groups round robin, warps 4.. = activation
+// producers (global -> pre-activation -> hi/lo fp16 split -> smem), last 8 warps = drain + fused intermediate + epilogue.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "tc_kernels.cuh"
+
+namespace adec {
+
+constexpr int F16_KB = TC_CP / 8;      // 16-byte K blocks (8 channels) per 32-channel piece and plane
+constexpr int F16_MIDP = 128;          // rows of the fused intermediate operand (one row per drain lane: 16-byte stores are conflict-free)
+constexpr float F16_LO_SCALE = 2048.f; // 2^11
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d),
+        "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+template <int NT, int PREC> struct TcfCfg {
+    static constexpr int NPR = PREC == 3 ? 3 : 1;                  // weight planes per tap: hi | lo | hi * 2^-11
+    static constexpr int NPL = PREC == 3 ? 2 : 1;                  // activation planes: hi | lo * 2^11
+    static constexpr int TAP_BYTES = NPR * F16_KB * NT * 16;       // one (piece, tap) of weights
+    static constexpr int STAGE_BYTES = 2 * TAP_BYTES;              // one group = up to two taps
+    static constexpr int STAGES = NT == 64 ? 4 : 3;
+    static constexpr int NW = (STAGES % 2) ? 3 : 2;                // MMA issuer warps (NW | STAGES, NW | NPB: the barrier rule)
+    static constexpr int NPB = NT == 128 ? (NW == 3 ? 3 : 4) : (NW == 3 ? 6 : 8);   // TMEM partials
+    static constexpr int MB = NT == 64 ? 2 : 1;                    // fused-intermediate buffers
+    static constexpr int NDG = 2;                                  // drain groups (NT=32: each owns half a 32-column piece)
+    static constexpr int NPROD = NT == 128 ? 128 : 256;            // activation-producer threads
+    static constexpr int DRAIN0 = (128 + NPROD) / 32;
+    static constexpr int THREADS = 128 + NPROD + 128 * NDG;
+    static constexpr int MID_BYTES = NPL * F16_KB * F16_MIDP * 16; // one intermediate piece (32 channels)
+    __host__ __device__ static constexpr int win_pitch(int wrows) { return ((wrows + 1) & ~3) + 2; }      // rows, == 2 mod 4: conflict-free producer stores
+    __host__ __device__ static constexpr int win_bytes(int wrows) { return NPL * F16_KB * win_pitch(wrows) * 16; }
+    // window buffers: as many as fit (2..4): the producers run that many pieces ahead of the MMAs
+    static int n_wbuf(int wrows, bool fuse) {
+        const long long avail = 227 * 1024 - 512 - (long long)STAGES * STAGE_BYTES - (fuse ? (long long)MB * MID_BYTES : 0);
+        const long long n = avail / win_bytes(wrows);
+        return (int)(n > 4 ? 4 : n);
+    }
+    static size_t smem_bytes(int wrows, bool fuse) {
+        return 512 + (size_t)STAGES * STAGE_BYTES + (size_t)n_wbuf(wrows, fuse) * win_bytes(wrows) + (fuse ? (size_t)MB * MID_BYTES : 0);
+    }
+};
+
+// 8 consecutive channels of one row -> one 16-byte hi block (+ one lo block)
+template <int PREC>
+__device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo, const float4 u, const float4 v) {
+    if (PREC == 3) {
+        const __half2 h0 = __floats2half2_rn(u.x, u.y), h1 = __floats2half2_rn(u.z, u.w), h2 = __floats2half2_rn(v.x, v.y), h3 = __floats2half2_rn(v.z, v.w);
+        const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
+        const __half2 l0 = __floats2half2_rn((u.x - f0.x) * F16_LO_SCALE, (u.y - f0.y) * F16_LO_SCALE);
+        const __half2 l1 = __floats2half2_rn((u.z - f1.x) * F16_LO_SCALE, (u.w - f1.y) * F16_LO_SCALE);
+        const __half2 l2 = __floats2half2_rn((v.x - f2.x) * F16_LO_SCALE, (v.y - f2.y) * F16_LO_SCALE);
+        const __half2 l3 = __floats2half2_rn((v.z - f3.x) * F16_LO_SCALE, (v.w - f3.y) * F16_LO_SCALE);
+        uint4 H, L;
+        H.x = *reinterpret_cast<const uint32_t*>(&h0); H.y = *reinterpret_cast<const uint32_t*>(&h1);
+        H.z = *reinterpret_cast<const uint32_t*>(&h2); H.w = *reinterpret_cast<const uint32_t*>(&h3);
+        L.x = *reinterpret_cast<const uint32_t*>(&l0); L.y = *reinterpret_cast<const uint32_t*>(&l1);
+        L.z = *reinterpret_cast<const uint32_t*>(&l2); L.w = *reinterpret_cast<const uint32_t*>(&l3);
+        *reinterpret_cast<uint4*>(hi) = H;
+        *reinterpret_cast<uint4*>(lo) = L;
+    } else {
+        const __nv_bfloat162 h0 = __floats2bfloat162_rn(u.x, u.y), h1 = __floats2bfloat162_rn(u.z, u.w), h2 = __floats2bfloat162_rn(v.x, v.y),
+                             h3 = __floats2bfloat162_rn(v.z, v.w);
+        uint4 H;
+        H.x = *reinterpret_cast<const uint32_t*>(&h0); H.y = *reinterpret_cast<const uint32_t*>(&h1);
+        H.z = *reinterpret_cast<const uint32_t*>(&h2); H.w = *reinterpret_cast<const uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(hi) = H;
+    }
+}
+
+__device__ __forceinline__ float4 norm4(float4 x, const float* mean, const float* scale) {
+    const float4 mu = *reinterpret_cast<const float4*>(mean);
+    const float4 sc = *reinterpret_cast<const float4*>(scale);
+    x.x = __fdiv_rn(x.x - mu.x, sc.x); x.y = __fdiv_rn(x.y - mu.y, sc.y);
+    x.z = __fdiv_rn(x.z - mu.z, sc.z); x.w = __fdiv_rn(x.w - mu.w, sc.w);
+    return x;
+}
+
+template <int NT, bool FUSE, int PRE, int PREC>
+__global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
+    using Cfg = TcfCfg<NT, PREC>;
+    constexpr int S = Cfg::STAGES, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG, KB = F16_KB, MIDP = F16_MIDP;
+    constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0, NPB = Cfg::NPB, MB = Cfg::MB, NW = Cfg::NW;
+    constexpr int STAGE_BYTES = Cfg::STAGE_BYTES, TAP_BYTES = Cfg::TAP_BYTES, PLANE_B = KB * NT * 16;   // one weight plane of one tap
+    constexpr int NCOL = NT / NDG;                       // accumulator registers per drain thread
+    constexpr bool HALF = NCOL < CP;                     // NT=32: a drain group owns 16 of the piece's 32 columns
+    constexpr int PPG = HALF ? 1 : NCOL / CP;            // 32-column pieces (or half pieces) owned by one drain group
+    constexpr int UC = HALF ? NCOL : CP;                 // columns per owned unit
+    constexpr bool PIPE = FUSE && NT == 32;              // conv of tile i+1 issued before the 1x1 conv of tile i
+    // instruction descriptor: D = f32 (1 << 4), A/B = f16 (0) or bf16 (1) at bits 7 / 10, both K-major, N >> 3 at 17, M >> 4 at 24
+    constexpr uint32_t FMT = PREC == 3 ? 0u : 1u;
+    constexpr uint32_t IDESC = (1u << 4) | (FMT << 7) | (FMT << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    static_assert(S % NW == 0 && NPB % NW == 0, "a weight stage / TMEM partial must belong to one MMA warp");
+    constexpr uint32_t TMEM_COLS = NPB * NT <= 32 ? 32 : NPB * NT <= 64 ? 64 : NPB * NT <= 128 ? 128 : NPB * NT <= 256 ? 256 : 512;
+    static_assert(NPB * NT <= 512, "TMEM has 512 columns");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t* b_full = reinterpret_cast<uint64_t*>(smem_raw);     // [S]   weights landed
+    uint64_t* b_empty = b_full + S;                                // [S]   weights consumed
+    uint64_t* w_full = b_empty + S;                                // [4]   window piece written (a.n_wbuf <= 4 buffers in use)
+    uint64_t* w_empty = w_full + 4;                                // [4]   window piece consumed
+    uint64_t* m_full = w_empty + 4;                                // [MB]  fused-intermediate piece written
+    uint64_t* m_empty = m_full + 2;                                // [2]   ... consumed; indexed by the drain group that writes the freed buffer NEXT
+    uint64_t* p_full = m_empty + 2;                                // [NPB] TMEM partial complete
+    uint64_t* p_empty = p_full + NPB;                              // [NPB] TMEM partial drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_empty + NPB);
+    unsigned char* bst = smem_raw + 512;                           // up to 40 barriers + the TMEM slot live in the first 512 B
+    const int wrows = TT + (a.Ktaps - 1) * a.dil;
+    const int wrp = Cfg::win_pitch(wrows);
+    const int win_b = Cfg::win_bytes(wrows);
+    unsigned char* wbuf0 = bst + S * STAGE_BYTES;                  // a.n_wbuf window buffers of win_b bytes
+    unsigned char* mbuf = wbuf0 + (size_t)a.n_wbuf * win_b;        // FUSE only: MB x MID_BYTES
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int gpp = (a.Ktaps + 1) >> 1;                            // groups per piece: tap pairs (+ one single tap)
+    const int n_g1 = a.n_pieces * gpp;
+    const int n_g2 = FUSE ? NT / CP : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], NW); }
+        for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
+        for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], NW);
+        for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
+        mbar_fence_init();
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------ weight producer: one bulk copy per group (1 or 2 taps)
+        if (lane == 0) {
+            int c = 0;
+            auto stream = [&](const unsigned char* base, int pieces, int taps) {
+                for (int p = 0; p < pieces; ++p)
+                    for (int t0 = 0; t0 < taps; t0 += 2, ++c) {
+                        const int s = c % S, it = c / S;
+                        const uint32_t bytes = (uint32_t)(taps - t0 >= 2 ? 2 : 1) * TAP_BYTES;
+                        if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1, 100);
+                        mbar_arrive_expect_tx(&b_full[s], bytes);
+                        bulk_g2s(bst + s * STAGE_BYTES, base + ((long long)p * taps + t0) * TAP_BYTES, bytes, &b_full[s]);
+                    }
+            };
+            const unsigned char* w1 = reinterpret_cast<const unsigned char*>(a.w);
+            const unsigned char* w2 = reinterpret_cast<const unsigned char*>(a.w2);
+            auto w1_of = [&](int tile) { return w1 + (long long)((tile / n_xtiles) % n_ytiles) * a.w_tile_floats * 4; };
+            if (PIPE) {
+                // same order as the MMA warps: G1(t0), then per tile { G1(next), G2(this) }
+                if ((int)blockIdx.x < n_tiles) stream(w1_of(blockIdx.x), a.n_pieces, a.Ktaps);
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    if (tile + (int)gridDim.x < n_tiles) stream(w1_of(tile + gridDim.x), a.n_pieces, a.Ktaps);
+                    stream(w2, n_g2, 1);
+                }
+            } else {
+                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                    stream(w1_of(tile), a.n_pieces, a.Ktaps);
+                    if (FUSE) stream(w2, n_g2, 1);
+                }
+            }
+        }
+    } else if (warp >= 1 && warp <= NW) {
+        // ------------------------------------------------ MMA issuers (groups round robin)
+        const int mw = warp - 1;
+        int c = 0, wp = 0, mp = 0;
+        const uint32_t b_lbo = (uint32_t)NT * 16u;
+        const uint32_t wbuf0_u = smem_u32(wbuf0), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
+        // one group: ntaps (1 or 2) taps of one 32-channel piece; tap t reads window rows shifted by row_off + t * tap_step bytes
+        auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off, uint32_t tap_step, int ntaps) {
+            const int s = c % S, pb = c % NPB;
+            mbar_wait(&b_full[s], (c / S) & 1, 300);
+            if (c >= NPB) mbar_wait(&p_empty[pb], ((c / NPB) - 1) & 1, 400);
+            tc_fence_after();
+            const uint32_t bw = bst_u + (uint32_t)s * STAGE_BYTES;
+            const uint32_t acc = tmem + (uint32_t)pb * NT;
+            if (elect_one()) {
+                uint32_t accum = 0u;
+                if (PREC == 3) {
+                    // small terms first: A_lo x W_his, A_hi x W_lo
+                    for (int t = 0; t < ntaps; ++t)
+#pragma unroll
+                        for (int ks = 0; ks < KB / 2; ++ks) {
+                            umma_f16(acc, umma_desc(a_lo + (uint32_t)(ks * 2) * lbo + row_off + t * tap_step, lbo),
+                                     umma_desc(bw + t * TAP_BYTES + 2 * PLANE_B + (uint32_t)(ks * 2) * b_lbo, b_lbo), IDESC, accum);
+                            accum = 1u;
+                        }
+                    for (int t = 0; t < ntaps; ++t)
+#pragma unroll
+                        for (int ks = 0; ks < KB / 2; ++ks)
+                            umma_f16(acc, umma_desc(a_hi + (uint32_t)(ks * 2) * lbo + row_off + t * tap_step, lbo),
+                                     umma_desc(bw + t * TAP_BYTES + PLANE_B + (uint32_t)(ks * 2) * b_lbo, b_lbo), IDESC, 1u);
+                }
+                for (int t = 0; t < ntaps; ++t)
+#pragma unroll
+                    for (int ks = 0; ks < KB / 2; ++ks) {
+                        umma_f16(acc, umma_desc(a_hi + (uint32_t)(ks * 2) * lbo + row_off + t * tap_step, lbo),
+                                 umma_desc(bw + t * TAP_BYTES + (uint32_t)(ks * 2) * b_lbo, b_lbo), IDESC, accum);
+                        accum = 1u;
+                    }
+                umma_commit(&b_empty[s]);
+                umma_commit(&p_full[pb]);
+            }
+            __syncwarp();
+        };
+        const uint32_t lbo1 = (uint32_t)wrp * 16u, lbo2 = (uint32_t)MIDP * 16u;
+        const uint32_t tap_step = (uint32_t)a.dil * 16u;
+        auto gemm1 = [&]() {        // one tile's conv over its window pieces
+            for (int p = 0; p < a.n_pieces; ++p, ++wp) {
+                const int buf = wp % a.n_wbuf;
+                mbar_wait(&w_full[buf], (wp / a.n_wbuf) & 1, 200);
+                const uint32_t a_hi = wbuf0_u + (uint32_t)buf * (uint32_t)win_b;
+                const uint32_t a_lo = a_hi + (uint32_t)KB * lbo1;
+                for (int t0 = 0; t0 < a.Ktaps; t0 += 2, ++c)
+                    if (c % NW == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)t0 * tap_step, tap_step, a.Ktaps - t0 >= 2 ? 2 : 1);
+                if (elect_one()) umma_commit(&w_empty[buf]);
+                __syncwarp();
+            }
+        };
+        auto gemm2 = [&]() {        // the fused 1x1 conv over the intermediate pieces
+            for (int p = 0; p < NT / CP; ++p, ++mp, ++c) {
+                const int mb = mp % MB;
+                mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
+                const uint32_t m_hi = mbuf_u + (uint32_t)mb * Cfg::MID_BYTES;
+                if (c % NW == mw) issue_group(m_hi, m_hi + (uint32_t)KB * lbo2, lbo2, 0u, 0u, 1);
+                // buffer mb is free for piece mp + MB, which drain group (mp + MB) % NDG writes: signal THAT group's barrier
+                if (elect_one()) umma_commit(&m_empty[HALF ? 0 : (mp + MB) % NDG]);
+                __syncwarp();
+            }
+        };
+        if (PIPE) {
+            if ((int)blockIdx.x < n_tiles) gemm1();
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                if (tile + (int)gridDim.x < n_tiles) gemm1();
+                gemm2();
+            }
+        } else {
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                gemm1();
+                if (FUSE) gemm2();
+            }
+        }
+    } else if (warp >= 4 && warp < DRAIN0) {
+        // ------------------------------------------------ activation producers: one item = 8 channels (32 B of global) of one window row.
+        // The loads of a piece are issued BEFORE the wait for a free window buffer, so global latency overlaps the MMAs that still read
+        // the buffer; a.n_wbuf (2..4) buffers let the producers run several pieces ahead.
+        const int pt = tid - 128;
+        int wp = 0;
+        constexpr int RPP = NPROD / KB;            // window rows per pass
+        constexpr int UNR = NPROD == 128 ? 5 : 3;  // rows in flight per thread (2 x 128-bit loads each): one pass covers 160 / 192 rows
+        const int c8 = pt & (KB - 1), m0 = pt >> 2;
+        const bool halves = a.RG > 1 && a.Cin < 8; // a 4-channel strided conv: the two halves of a block are different x~ rows
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
+            const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+            const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
+            const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
+            for (int p = 0; p < a.n_pieces; ++p, ++wp) {
+                const int buf = wp % a.n_wbuf;
+                unsigned char* hi = wbuf0 + (size_t)buf * win_b + (size_t)c8 * wrp * 16;
+                unsigned char* lo = hi + (size_t)KB * wrp * 16;
+                const int q = p * CP + c8 * 8;
+                int r = 0, ci = q;
+                if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
+                const long long i_first = (long long)j0 * a.RG + r;
+                const long long i_last = (long long)(j0 + wrows - 1) * a.RG + r;
+                bool waited = wp < a.n_wbuf;
+                if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM && !halves) {
+                    // interior piece: every row comes from the chunk
+                    const float* xp = xg + ci + (i_first - a.P + (long long)m0 * a.RG) * a.ldx;
+                    const long long xstep = (long long)RPP * a.RG * a.ldx;
+                    for (int mb = m0; mb < wrows; mb += RPP * UNR, xp += xstep * UNR) {
+                        float4 u[UNR], v[UNR];
+#pragma unroll
+                        for (int k = 0; k < UNR; ++k)
+                            if (mb + k * RPP < wrows) {
+                                u[k] = __ldg(reinterpret_cast<const float4*>(xp + k * xstep));
+                                v[k] = __ldg(reinterpret_cast<const float4*>(xp + k * xstep) + 1);
+                            }
+                        if (!waited) { mbar_wait(&w_empty[buf], ((wp / a.n_wbuf) - 1) & 1, 500); waited = true; }
+#pragma unroll
+                        for (int k = 0; k < UNR; ++k) {
+                            const int m = mb + k * RPP;
+                            if (m < wrows) split_store<PREC>(hi + m * 16, lo + m * 16, apply_act_t<PRE>(u[k], a.slope), apply_act_t<PRE>(v[k], a.slope));
+                        }
+                    }
+                } else {
+                    // edge piece: rows from the causal state (stored post-activation), the chunk, or beyond its end (zeros)
+                    int ci2 = ci + 4;
+                    for (int mb = m0; mb < wrows; mb += RPP * UNR) {
+                        float4 u[UNR], v[UNR];
+                        unsigned act = 0u;
+#pragma unroll
+                        for (int k = 0; k < UNR; ++k) {
+                            const int m = mb + k * RPP;
+                            u[k] = v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (m < wrows) {
+#pragma unroll
+                                for (int hf = 0; hf < 2; ++hf) {
+                                    int rr = r, cc = ci + 4 * hf;
+                                    if (halves) { rr = (q + 4 * hf) >> a.lgCin; cc = (q + 4 * hf) & (a.Cin - 1); if (hf) ci2 = cc; }
+                                    const long long i = (long long)(j0 + m) * a.RG + rr;
+                                    long long ti = i - a.P;
+                                    if (a.hist_rep && ti < 0) ti = 0;              // non-streaming transposed conv: replicate the first input row
+                                    float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                                    if (ti < 0) w4 = __ldg(reinterpret_cast<const float4*>(sg + i * a.st_ld + cc));
+                                    else if (ti < a.T) { w4 = __ldg(reinterpret_cast<const float4*>(xg + ti * a.ldx + cc)); act |= 1u << (2 * k + hf); }
+                                    if (hf) v[k] = w4; else u[k] = w4;
+                                }
+                            }
+                        }
+                        if (!waited) { mbar_wait(&w_empty[buf], ((wp / a.n_wbuf) - 1) & 1, 500); waited = true; }
+#pragma unroll
+                        for (int k = 0; k < UNR; ++k) {
+                            const int m = mb + k * RPP;
+                            if (m < wrows) {
+                                float4 x0 = u[k], x1 = v[k];
+                                if ((act >> (2 * k)) & 1u) x0 = PRE == ACT_NORM ? norm4(x0, a.mean + ci, a.scale + ci) : apply_act_t<PRE>(x0, a.slope);
+                                if ((act >> (2 * k)) & 2u) x1 = PRE == ACT_NORM ? norm4(x1, a.mean + ci2, a.scale + ci2) : apply_act_t<PRE>(x1, a.slope);
+                                split_store<PREC>(hi + m * 16, lo + m * 16, x0, x1);
+                            }
+                        }
+                    }
+                }
+                fence_async_smem();
+                mbar_arrive(&w_full[buf]);
+            }
+            // ---- new causal state (conv_layer.py:155)
+            if (xt == (a.Tout - 1) / TT && co_tile == 0 && g < a.st_groups && a.P > 0) {
+                float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
+                const int nvec = a.P * (a.Cin / 4);
+                for (int idx = pt; idx < nvec; idx += NPROD) {
+                    const int r = idx / (a.Cin / 4);
+                    const int cc = (idx - r * (a.Cin / 4)) * 4;
+                    const long long i = (long long)a.T + r;
+                    float4 w4;
+                    if (i < a.P) {
+                        w4 = *reinterpret_cast<const float4*>(sg + i * a.st_ld + cc);
+                    } else {
+                        w4 = __ldg(reinterpret_cast<const float4*>(xg + (i - a.P) * a.ldx + cc));
+                        if (PRE == ACT_NORM) w4 = norm4(w4, a.mean + cc, a.scale + cc);
+                        else w4 = apply_act_t<PRE>(w4, a.slope);
+                    }
+                    *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + cc) = w4;
+                }
+            }
+        }
+    } else if (warp >= DRAIN0) {
+        // ------------------------------------------------ drain warps: register accumulation, fused intermediate, epilogue
+        const int dg = (warp - DRAIN0) >> 2;
+        const int row = (warp & 3) * 32 + lane;
+        const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+        float racc[NCOL];
+        constexpr bool PREFETCH_RES = FUSE && NT <= 64;     // registers permitting
+        float4 rpre[PREFETCH_RES ? PPG : 1][UC / 4];
+        int c = 0, mq = 0;
+        int m_waits = 0;
+        float vmax = 0.f;                                   // largest magnitude this thread produced (fp16-split range check)
+        auto drain = [&](float (&acc)[NCOL], int ngroups) {
+            for (int gi = 0; gi < ngroups; ++gi, ++c) {
+                const int pb = c % NPB;
+                mbar_wait(&p_full[pb], (c / NPB) & 1, 600);
+                tc_fence_after();
+                if (HALF) {
+                    uint32_t r0[16];
+                    tmem_ld16(tmem + lane_base + (uint32_t)pb * NT + (uint32_t)dg * UC, r0);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] = __fadd_rn(acc[i], __uint_as_float(r0[i]));
+                } else {
+#pragma unroll
+                    for (int pl = 0; pl < PPG; ++pl) {
+                        const uint32_t taddr = tmem + lane_base + (uint32_t)pb * NT + (uint32_t)(pl * NDG + dg) * CP;
+                        uint32_t r0[16], r1[16];
+                        tmem_ld16(taddr, r0);
+                        tmem_ld16(taddr + 16, r1);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            acc[pl * UC + i] = __fadd_rn(acc[pl * UC + i], __uint_as_float(r0[i]));
+                            acc[pl * UC + 16 + i] = __fadd_rn(acc[pl * UC + 16 + i], __uint_as_float(r1[i]));
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&p_empty[pb]);
+            }
+        };
+        float oacc[PIPE ? NCOL : 1];                         // PIPE: 1x1-conv sums of tile i while racc already holds tile i+1
+        if (PIPE && (int)blockIdx.x < n_tiles) {
+#pragma unroll
+            for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+            drain(racc, n_g1);                                // conv of the first tile
+        }
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
+            const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+            if (!PIPE) {
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+                drain(racc, n_g1);
+            }
+            if (FUSE) {
+                // weight scale out, activation (registers only), so that it overlaps the wait for a free intermediate buffer
+#pragma unroll
+                for (int i = 0; i < NCOL; i += 4) {
+                    const float4 m4 = apply_act_t<PRE>(make_float4(racc[i] * a.w_scale, racc[i + 1] * a.w_scale, racc[i + 2] * a.w_scale, racc[i + 3] * a.w_scale), a.slope);
+                    racc[i] = m4.x; racc[i + 1] = m4.y; racc[i + 2] = m4.z; racc[i + 3] = m4.w;
+                    vmax = fmaxf(vmax, fmaxf(fmaxf(fabsf(m4.x), fabsf(m4.y)), fmaxf(fabsf(m4.z), fabsf(m4.w))));
+                }
+                // intermediate pieces in consumption order 0,1,2,...: piece q is written by group q % NDG (both groups at NT=32)
+                // into buffer Q % MB (Q = running piece index), which is free once piece Q-MB was consumed; the MMA warps signal
+                // that on the writing group's own m_empty barrier, so the k-th wait of a thread is for that barrier's k-th phase.
+#pragma unroll
+                for (int q = 0; q < NT / CP; ++q) {
+                    const int Q = mq + q, mb = Q % MB;
+                    if (HALF || q % NDG == dg) {
+                        if (Q >= MB) { mbar_wait(&m_empty[HALF ? 0 : dg], m_waits & 1, 700); ++m_waits; }
+                        const int pl = HALF ? 0 : q / NDG;
+                        unsigned char* hi = mbuf + mb * Cfg::MID_BYTES;
+                        unsigned char* lo = hi + KB * MIDP * 16;
+#pragma unroll
+                        for (int u = 0; u < UC / 8; ++u) {
+                            const int kb = HALF ? dg * (UC / 8) + u : u;       // 16-byte channel block inside the 32-channel piece
+                            const float* s8 = racc + pl * UC + u * 8;
+                            split_store<PREC>(hi + (kb * MIDP + row) * 16, lo + (kb * MIDP + row) * 16, make_float4(s8[0], s8[1], s8[2], s8[3]),
+                                              make_float4(s8[4], s8[5], s8[6], s8[7]));
+                        }
+                        fence_async_smem();
+                        mbar_arrive(&m_full[mb]);
+                    }
+                }
+                mq += NT / CP;
+#pragma unroll
+                for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
+                if (PREFETCH_RES && a.res && j0 + row < a.Tout) {
+                    // the skip tensor's rows are known now: fetch them while the MMAs run
+#pragma unroll
+                    for (int pl = 0; pl < PPG; ++pl) {
+                        const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
+                        const float* rp = a.res + (long long)b * a.res_bs + (long long)(j0 + row) * a.ldr + g * a.r_goff + co_l;
+#pragma unroll
+                        for (int i = 0; i < UC / 4; ++i) rpre[pl][i] = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                    }
+                }
+                if (PIPE) {
+                    // partials arrive in MMA issue order: the NEXT tile's conv first (into racc), then this tile's 1x1 conv
+                    if (tile + (int)gridDim.x < n_tiles) drain(racc, n_g1);
+#pragma unroll
+                    for (int i = 0; i < (PIPE ? NCOL : 1); ++i) oacc[i] = 0.f;
+                    drain(reinterpret_cast<float (&)[NCOL]>(oacc), n_g2);
+                } else {
+                    drain(racc, n_g2);
+                }
+            }
+            float* const outv = PIPE ? oacc : racc;
+            const float oscale = FUSE ? a.w2_scale : a.w_scale;
+            // ---- epilogue: row `row` of the tile, this group's PPG pieces of 32 channels
+            const int t = j0 + row;
+            if (t < a.Tout) {
+#pragma unroll
+                for (int pl = 0; pl < PPG; ++pl) {
+                    const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
+                    if (co_l >= a.Cout_g) continue;            // zero-padded part of a channel tile (e.g. 96 outputs in a 128-wide tile)
+                    float* v = outv + pl * UC;
+#pragma unroll
+                    for (int i = 0; i < UC; ++i) v[i] *= oscale;
+                    if (a.bias) {
+#pragma unroll
+                        for (int i = 0; i < UC / 4; ++i) {
+                            const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.bias + g * a.Cout_g + co_l) + i);
+                            v[4 * i] += b4.x; v[4 * i + 1] += b4.y; v[4 * i + 2] += b4.z; v[4 * i + 3] += b4.w;
+                        }
+                    }
+                    if (a.res) {
+                        const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
+                        float4 r4[UC / 4];
+#pragma unroll
+                        for (int i = 0; i < UC / 4; ++i)
+                            r4[i] = PREFETCH_RES ? rpre[PREFETCH_RES ? pl : 0][i] : __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
+#pragma unroll
+                        for (int i = 0; i < UC / 4; ++i) {
+                            v[4 * i] = r4[i].x + v[4 * i]; v[4 * i + 1] = r4[i].y + v[4 * i + 1];
+                            v[4 * i + 2] = r4[i].z + v[4 * i + 2]; v[4 * i + 3] = r4[i].w + v[4 * i + 3];
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < UC; ++i) vmax = fmaxf(vmax, fabsf(v[i]));
+                    if (a.out_nct) {
+                        float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
+#pragma unroll
+                        for (int i = 0; i < UC; ++i) yp[(long long)i * a.Tout] = v[i];
+                    } else {
+                        float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
+#pragma unroll
+                        for (int i = 0; i < UC / 4; ++i)
+                            *(reinterpret_cast<float4*>(yp) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                }
+            }
+        }
+        // every activation is some launch's output: one check here bounds the operands of the next launch's fp16 split
+        if (PREC == 3 && a.err && !(vmax < 60000.f)) atomicOr(a.err, 2);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+}
+
+}  // namespace adec

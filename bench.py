@@ -51,14 +51,56 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons DURING the timed region (B200_PROFILING.md recipe).  Default source is NVML in a
+    thread of this process (the library nvidia-smi itself reads; no subprocess, 20 ms period); ADEC_BENCH_SAMPLER=smi runs the
+    recipe's `nvidia-smi -lms 100` loop instead, =off disables sampling."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # nvmlClocksEventReasons bits (nvml.h)
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index, self.rows, self.proc = index, [], None
+        self.mode = os.environ.get("ADEC_BENCH_SAMPLER", "nvml")
+        self._stop = threading.Event()
+        self._thread = None
 
     def start(self):
+        if self.mode == "off":
+            return
+        if self.mode == "nvml":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                # CUDA_VISIBLE_DEVICES may renumber: address the device by its PCI bus id
+                import torch
+                pr = torch.cuda.get_device_properties(self.index)
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(f"{pr.pci_domain_id:08x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0")
+                except Exception:
+                    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                    phys = int(vis.split(",")[self.index]) if vis and all(v.strip().isdigit() for v in vis.split(",")) else self.index
+                    h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+                self._max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+
+                def loop():
+                    while not self._stop.is_set():
+                        try:
+                            sm = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                            pw = pynvml.nvmlDeviceGetPowerUsage(h) / 1e3
+                            try:
+                                rs = int(pynvml.nvmlDeviceGetCurrentClocksEventReasons(h))
+                            except Exception:
+                                rs = int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                            self.rows.append((time.time(), (sm, pw, rs)))
+                        except Exception:
+                            pass
+                        self._stop.wait(0.02)
+                self._thread = threading.Thread(target=loop, daemon=True)
+                self._thread.start()
+                return
+            except Exception:
+                self.mode = "smi"          # NVML binding unavailable: fall back to the nvidia-smi loop
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
@@ -71,6 +113,17 @@ class ClockSampler:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self, t0, t1):
+        if self.mode == "off":
+            return {"sampler": "off"}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=1.0)
+            rows = [r for (t, r) in self.rows if t0 <= t <= t1] or [r for (_, r) in self.rows]
+            if not rows:
+                return None
+            reasons = sorted({name for (_, _, rs) in rows for name, bit in self.REASONS if rs & bit})
+            return {"sm_mhz": statistics.median(r[0] for r in rows), "sm_max_mhz": self._max, "reasons": reasons,
+                    "samples": len(rows), "power_w_max": max(r[1] for r in rows), "sampler": "nvml, 20 ms period, in-process thread"}
         if self.proc is None:
             return None
         time.sleep(0.15)
@@ -86,7 +139,7 @@ class ClockSampler:
                     if r[col].lower().startswith("active"):
                         reasons.add(name)
             return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": sorted(reasons),
-                    "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+                    "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows), "sampler": "nvidia-smi -lms 100"}
         except Exception:
             return None
 

@@ -61,6 +61,9 @@ typedef struct adec_config {
     /* appended in round 1 (variants of SURVEY.md 8(f) rank 1) */
     int codec_activate;                                    /* symAAD: codec='activate_audiodec' (encoder.py:145-175, decoder.py:151-214) */
     int n_resblocks;  int resblock_kernel_sizes[ADEC_MAX_STAGES];   /* AD v0: MultiReceptiveField, one residual block per kernel size */
+    /* appended in round 2 */
+    int compute_dtype;                                     /* 0 = fp32-grade (default); 1 = bf16 conv operands with fp32 accumulation, HiFi-GAN vocoder
+                                                              only: what `decoder.to(torch.bfloat16)` asks of the reference (BASELINE configs[2]) */
 } adec_config;
 
 /* -- lifetime ---------------------------------------------------------------- */
@@ -82,7 +85,9 @@ int adec_finalize(adec_handle *h);
 
 /* -- per-stream causal state -------------------------------------------------- */
 int adec_n_streams(const adec_handle *h);
-/* n == current: no-op.  current == 1: replicate that stream's state n times.  otherwise error. */
+/* n == current: no-op.  current == 1: that (warmed) stream's state is replicated n times.  current > 1: streams [0, min(n, current))
+ * keep their state, streams added beyond `current` start from zero history (what reset_buffer() leaves).  Buffers are resized and
+ * the replaced ones freed. */
 int adec_set_streams(adec_handle *h, int n_streams);
 /* reset_buffer() (AudioDec.py:250-256, HiFiGAN.py:298-305): zero all history, keep n_streams. */
 int adec_reset(adec_handle *h, void *stream);
@@ -129,9 +134,18 @@ int adec_unpack_indices(adec_handle *h, const uint8_t *packed, int B, int F, int
 /* synchronises `stream`, then returns and clears the handle's device-side flag: 1 if lookup / pack / unpack met an
  * out-of-range index since the last call (the reference's F.embedding would have raised, vq_module.py:160), -1 on error */
 int adec_index_error(adec_handle *h, void *stream);
+/* same protocol for the conv engine's range flag: 1 if an activation reached |a| >= 6e4 since the last call.  The default engine
+ * multiplies fp16 pieces of the fp32 activations (tc_f16.cuh); the reference's fp32 convs (layers/conv_layer.py:55-64) have no such
+ * bound, so a model that gets there must run with ADEC_CONV_PATH=tf32.  adec_codec_host checks both flags itself. */
+int adec_range_error(adec_handle *h, void *stream);
 
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t adec_launch_count(const adec_handle *h);
+
+/* Measured compute ceiling of the conv engine for bench.py's roofline: every SM streams `n_groups` x 12 tcgen05.mma (M = 128, N = NT,
+ * kind 0 = tf32 / 1 = f16) from shared-memory operands in the engine's layout, nothing else; *tflops = dense TFLOP/s, *ms = duration
+ * (may be NULL).  No handle needed. */
+int adec_probe_mma(int device, int kind, int NT, int n_groups, double *tflops, double *ms);
 
 /* Per-launch CUDA-event timing on the handle's stream (bench.py's roofline leg).  adec_profile(h,1) starts
  * recording around every kernel launch, adec_profile(h,0) stops and clears.  adec_profile_report writes one line

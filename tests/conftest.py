@@ -47,9 +47,9 @@ def hifigan_sd():
     return S.hifigan_state_dict(seed=1)
 
 
-@pytest.fixture(params=["tc", "ffma"])
+@pytest.fixture(params=["f16", "tf32", "ffma"])
 def conv_path(request, monkeypatch):
-    """Both conv engines behind the same C ABI: tcgen05 3xTF32 (default) and the CUDA-core FFMA kernels.  The library
-    reads ADEC_CONV_PATH when a handle is created."""
+    """The conv engines behind the same C ABI: tcgen05 kind::f16 with fp16-split operands (default), the round-1 tcgen05 3xTF32
+    kernels and the CUDA-core FFMA kernels.  The library reads ADEC_CONV_PATH when a handle is created."""
     monkeypatch.setenv("ADEC_CONV_PATH", request.param)
     return request.param

@@ -119,8 +119,23 @@ def test_quantize_bit_exact_vs_oracle_same_z(symad_sd):
     np.testing.assert_array_equal(zq.numpy(), orc.lookup(ridx).numpy() if bad.sum() == 0 else zq.numpy())
 
 
-def test_batch_vs_oracle_seeded(symad_sd):
-    """BASELINE config 2 shape at reduced size: 8 x 0.5 s through the whole path vs the oracle."""
+def _first_mismatch_margins(idx, ridx, margins):
+    """(Nq,B,F) indices: per frame with a differing code, the reference's own relative top-2 margin at the FIRST differing stage
+    (later stages of that frame quantise a different residual, so their margins say nothing)."""
+    bad = (idx != ridx)
+    out = []
+    for b, f in zip(*torch.nonzero(bad.any(0), as_tuple=True)):
+        i = int(torch.nonzero(bad[:, b, f])[0])
+        out.append(float(margins[i, b, f]))
+    return out
+
+
+MARGIN_TOL = 1e-6     # a differing decision is only accepted on a numerical tie of the reference itself
+
+
+def test_batch_vs_oracle_seeded(symad_sd, conv_path):
+    """BASELINE config 2 shape at reduced size: 8 x 0.5 s through the whole path vs the oracle.  Indices must be equal; a
+    differing frame is accepted only where the reference's own top-2 margin at the first differing stage is a tie (< 1e-6)."""
     from oracle import audiodec_oracle as O
     tx, rx, dec, _ = _codec(symad_sd)
     torch.manual_seed(1337)
@@ -128,12 +143,36 @@ def test_batch_vs_oracle_seeded(symad_sd):
     z, idx, zq, y = _run(tx, rx, dec, x)
     ref = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
     rz, ridx, rzq, ry = ref.run(x)
-    _, margins = ref.tx_encoder.quantize(rz, return_margins=True) if False else (None, None)
     np.testing.assert_allclose(z.numpy(), rz.numpy(), atol=Z_TOL)
-    frames_bad = (idx != ridx).any(0)
-    assert frames_bad.float().mean().item() <= 0.002, "more than 0.2% of frames have a differing code"
-    ok = ~frames_bad
+    _, _, margins = O.rvq_forward_index(rz.transpose(1, 2), ref.tx_encoder.embeds, return_margins=True)
+    ties = _first_mismatch_margins(idx, ridx, margins)
+    print(f"[parity] {conv_path}: {len(ties)} of {idx.shape[1] * idx.shape[2]} frames differ; reference margins there: {sorted(ties)[:8]}; "
+          f"smallest margin overall {margins.min().item():.3e}; z max-abs err {(z - rz).abs().max().item():.3e}")
+    assert all(m < MARGIN_TOL for m in ties), f"{len(ties)} frames differ beyond a tie: margins {sorted(ties, reverse=True)[:8]}"
+    ok = ~(idx != ridx).any(0)
     err = (y - ry).abs()[:, 0].reshape(8, -1, 300)[ok].max().item()
+    assert err <= WAVE_TOL, err
+
+
+def test_full_size_batch_vs_oracle(symad_sd):
+    """BASELINE configs[1] at FULL size (64 x 48000, the benchmarked batch, seed 1337): utterances 0, 21, 42 and 63 of the batch
+    against the oracle run on those rows (demoFile.py:58-61 per utterance): indices equal, waveform within 1e-4."""
+    from oracle import audiodec_oracle as O
+    tx, rx, dec, _ = _codec(symad_sd)
+    torch.manual_seed(1337)
+    x = 0.1 * torch.randn(64, 1, 48000)
+    z, idx, zq, y = _run(tx, rx, dec, x)
+    sel = [0, 21, 42, 63]
+    ref = O.CodecOracle(S.SYMAD_PARAMS, symad_sd)
+    rz, ridx, rzq, ry = ref.run(x[sel])
+    _, _, margins = O.rvq_forward_index(rz.transpose(1, 2), ref.tx_encoder.embeds, return_margins=True)
+    ties = _first_mismatch_margins(idx[:, sel], ridx, margins)
+    print(f"[parity] full size: {len(ties)} of {len(sel) * idx.shape[2]} frames differ; margins {sorted(ties)[:8]}; "
+          f"z max-abs err {(z[sel] - rz).abs().max().item():.3e}")
+    assert all(m < MARGIN_TOL for m in ties), f"frames differ beyond a tie: margins {sorted(ties, reverse=True)[:8]}"
+    ok = ~(idx[:, sel] != ridx).any(0)
+    err = (y[sel] - ry).abs()[:, 0].reshape(len(sel), -1, 300)[ok].max().item()
+    print(f"[parity] full size: waveform max-abs err {err:.3e}")
     assert err <= WAVE_TOL, err
 
 

@@ -240,6 +240,36 @@ class SymADStreamGenerator(_StreamGeneratorBase):
         _check(self._lib.adec_quantize(self._h, _ptr(z), b, f, _ptr(idx), self._stream()), self._h)
         return idx.squeeze(1) if b == 1 else idx
 
+    def quantize_fused(self, z, want_idx=True, want_packed=False, want_zq=True):
+        """quantize -> [pack] -> lookup in ONE launch (adec_quantize_ex): returns (idx or None, packed or None, zq or None) with the
+        shapes of quantize() / pack() / lookup().  Bit-identical to the three separate calls."""
+        self._ready()
+        self._want(z, "quantize_fused", 1, self.code_dim)
+        z = self._in(z)
+        b, _, f = z.shape
+        idx = torch.empty(self.codebook_num, b, f, device=self._device, dtype=torch.int64) if want_idx else None
+        packed = torch.empty(b, f, self.packed_frame_bytes(), device=self._device, dtype=torch.uint8) if want_packed else None
+        zq = torch.empty(b, f, self.code_dim, device=self._device, dtype=torch.float32) if want_zq else None
+        _check(self._lib.adec_quantize_ex(self._h, _ptr(z), b, f, _ptr(idx) if want_idx else None, _ptr(packed) if want_packed else None,
+                                          _ptr(zq) if want_zq else None, self._stream()), self._h)
+        if b == 1:
+            idx = idx.squeeze(1) if idx is not None else None
+            packed = packed.squeeze(0) if packed is not None else None
+        return idx, packed, zq
+
+    def lookup_packed(self, packed):
+        """uint8 (F,bytes) -> zq (1,F,D); (B,F,bytes) -> (B,F,D): lookup straight from the bitstream (unpack fused into lookup)."""
+        self._ready()
+        packed = self._in(packed, torch.uint8)
+        if packed.dim() == 2:
+            packed = packed.unsqueeze(0)
+        b, f, nb = packed.shape
+        if nb != self.packed_frame_bytes():
+            raise RuntimeError(f"audiodec_b200: lookup_packed: expected {self.packed_frame_bytes()} bytes per frame, got {nb}")
+        zq = torch.empty(b, f, self.code_dim, device=self._device, dtype=torch.float32)
+        _check(self._lib.adec_lookup_packed(self._h, _ptr(packed), b, f, _ptr(zq), self._stream()), self._h)
+        return zq
+
     def lookup(self, idx):
         """idx (Nq,F) -> zq (1,F,D); (Nq,B,F) -> (B,F,D)   (AudioDec.py:242-243)"""
         self._ready()

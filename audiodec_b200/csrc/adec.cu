@@ -244,6 +244,7 @@ struct adec_handle {
     int engine = 2;               // ADEC_CONV_PATH: 2 = f16 (tcgen05 kind::f16, default), 1 = tf32 (round-1 3xTF32), 0 = ffma (CUDA cores)
     bool use_tc = true;           // any tensor-core engine
     bool bf16 = false;            // cfg.compute_dtype == 1: bf16 operands (HiFi-GAN vocoder, f16 engine only)
+    bool stack_rows = true;       // ADEC_STACK_ROWS=0: never stack several streams' rows into one tile (A/B)
     int n_sms = 148;
     DevBuf ws[3];
     std::vector<void*> owned;     // device allocations freed in destroy
@@ -713,6 +714,16 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
                 const int wrows = TC_TT + (op.Ktaps - 1) * op.dil;
                 const int NT = op.tcf ? op.tcf->NT : op.tc->NT;
                 dim3 grid((Tout + TC_TT - 1) / TC_TT, op.G * op.n_co_tiles, rc.B);
+                a.n_streams = rc.B;
+                if (op.tcf && h->stack_rows) {
+                    // fill the 128-row tiles across streams when that needs fewer tiles (short chunks: 256 streams x 5..25 rows per layer)
+                    const long long L = (long long)Tout + (long long)(op.Ktaps - 1) * op.dil;
+                    const long long stacked = (rc.B * L + TC_TT - 1) / TC_TT;
+                    if (stacked < (long long)grid.x * rc.B && rc.B * L < (1ll << 30)) {
+                        a.stack_L = (int)L;
+                        grid = dim3((unsigned)stacked, grid.y, 1);
+                    }
+                }
                 const long long n_tiles = (long long)grid.x * grid.y * grid.z;
                 const int n_ctas = (int)std::min<long long>(n_tiles, h->n_sms);
                 size_t psmem;
@@ -1125,6 +1136,7 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
         else { g_create_error = std::string("ADEC_CONV_PATH must be f16, tf32 or ffma, not ") + pth; delete h; return 1; }
     }
     h->use_tc = h->engine != 0;
+    if (const char* sr = getenv("ADEC_STACK_ROWS")) h->stack_rows = atoi(sr) != 0;
     h->bf16 = cfg->compute_dtype == 1;
     if (cfg->compute_dtype != 0 && cfg->compute_dtype != 1) { g_create_error = "compute_dtype must be 0 (fp32) or 1 (bf16)"; delete h; return 1; }
     if (h->bf16 && (cfg->model_type != ADEC_MODEL_HIFIGAN || h->engine != 2)) {
@@ -1300,33 +1312,81 @@ int adec_decode_offline(adec_handle* h, const float* zq, int B, int F, float* y,
     return run_ops(h, h->dec_ops, rc, F, nullptr);
 }
 
-int adec_quantize(adec_handle* h, const float* z, int B, int F, int64_t* idx, void* stream) {
+static int index_bits(int n) { int b = 1; while ((1 << b) < n) ++b; return b; }
+
+int adec_packed_frame_bytes(const adec_handle* h) {
+    if (!h || h->cfg.model_type != ADEC_MODEL_SYMAD) return -1;
+    return (h->cfg.codebook_num * index_bits(h->cfg.codebook_size) + 7) / 8;
+}
+
+// residual VQ launch: pick frames-per-pass FP and passes per block so that the grid is ONE wave with the smallest idle tail
+extern "C++" template <int FP>
+cudaError_t launch_rvq(const adec_handle* h, RvqArgs a, cudaStream_t s, int* cost) {
+    static int per_sm[64] = {0};
+    auto kern = rvq_kernel<64, 4, FP>;
+    const int dev = h->device;
+    const auto smem_of = [&](int n_pass) { const int FR = n_pass * FP; return (size_t)FR * (2 * 64 + 1 + 2 * (RVQ_THREADS / 32) + a.nq) * 4; };
+    if (dev < 64 && !per_sm[dev]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        int nb = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, RVQ_THREADS, smem_of(2));
+        per_sm[dev] = std::max(1, nb);
+    }
+    const long long nfr = (long long)a.B * a.F, slots = (long long)h->n_sms * per_sm[dev < 64 ? dev : 0];
+    int n_pass = (int)((nfr + slots * FP - 1) / (slots * FP));
+    n_pass = std::max(1, std::min(n_pass, 96 / FP));                 // <= 96 frames of residuals + zq in shared memory
+    if (cost) { *cost = n_pass * (FP + 2) * (int)((nfr + slots * n_pass * FP - 1) / (slots * n_pass * FP)); return cudaSuccess; }
+    a.n_pass = n_pass;
+    const long long FR = (long long)n_pass * FP;
+    kern<<<(unsigned)((nfr + FR - 1) / FR), RVQ_THREADS, smem_of(n_pass), s>>>(a);
+    return cudaGetLastError();
+}
+
+int adec_quantize_ex(adec_handle* h, const float* z, int B, int F, int64_t* idx, uint8_t* packed, float* zq, void* stream) {
     if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
     if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail("quantize: not a symAD handle");
     if (B < 1 || F < 1) return h->fail("quantize: empty input");
+    if (!idx && !packed && !zq) return h->fail("quantize: no output requested");
     DeviceGuard dg(h->device);
     RvqArgs a{};
     a.z = z; a.B = B; a.F = F; a.nq = h->cfg.codebook_num; a.embed = h->d_embed; a.e2 = h->d_e2; a.idx = (long long*)idx;
-    const long long nfr = (long long)B * F;
-    rvq_kernel<64, 4><<<(unsigned)((nfr + RVQ_FRAMES - 1) / RVQ_FRAMES), RVQ_THREADS, 0, (cudaStream_t)stream>>>(a);
-    CK(h, cudaGetLastError());
+    a.packed = packed; a.zq = zq; a.bits = index_bits(h->cfg.codebook_size); a.bpf = adec_packed_frame_bytes(h);
+    int c16 = 0, c12 = 0, c8 = 0;
+    launch_rvq<16>(h, a, nullptr, &c16); launch_rvq<12>(h, a, nullptr, &c12); launch_rvq<8>(h, a, nullptr, &c8);
+    cudaError_t e = (c12 <= c16 && c12 <= c8) ? launch_rvq<12>(h, a, (cudaStream_t)stream, nullptr)
+                  : (c16 <= c8)               ? launch_rvq<16>(h, a, (cudaStream_t)stream, nullptr)
+                                              : launch_rvq<8>(h, a, (cudaStream_t)stream, nullptr);
+    if (e != cudaSuccess) return h->fail(fmt("launch of rvq_kernel failed: %s", cudaGetErrorString(e)));
     ++h->launches;
     return 0;
 }
 
-int adec_lookup(adec_handle* h, const int64_t* idx, int B, int F, float* zq, void* stream) {
+int adec_quantize(adec_handle* h, const float* z, int B, int F, int64_t* idx, void* stream) {
+    return adec_quantize_ex(h, z, B, F, idx, nullptr, nullptr, stream);
+}
+
+static int lookup_common(adec_handle* h, const int64_t* idx, const uint8_t* packed, int B, int F, float* zq, void* stream) {
     if (!h || !h->finalized) return h ? h->fail("not finalized") : 1;
     if (h->cfg.model_type != ADEC_MODEL_SYMAD) return h->fail("lookup: not a symAD handle");
     if (B < 1 || F < 1) return h->fail("lookup: empty input");
     DeviceGuard dg(h->device);
     LookupArgs a{};
-    a.idx = (const long long*)idx; a.nfr = (long long)B * F; a.nq = h->cfg.codebook_num; a.D = h->cfg.code_dim;
+    a.idx = (const long long*)idx; a.packed = packed; a.nfr = (long long)B * F; a.nq = h->cfg.codebook_num; a.D = h->cfg.code_dim;
+    a.N = h->cfg.codebook_size; a.bits = index_bits(a.N); a.bpf = adec_packed_frame_bytes(h);
     a.codebook = h->d_codebook; a.n_rows = (long long)h->cfg.codebook_num * h->cfg.codebook_size; a.zq = zq; a.err = h->d_err;
     const long long nth = a.nfr * (a.D / 4);
     lookup_kernel<<<(unsigned)((nth + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a);
     CK(h, cudaGetLastError());
     ++h->launches;
     return 0;
+}
+
+int adec_lookup(adec_handle* h, const int64_t* idx, int B, int F, float* zq, void* stream) {
+    return lookup_common(h, idx, nullptr, B, F, zq, stream);
+}
+
+int adec_lookup_packed(adec_handle* h, const uint8_t* packed, int B, int F, float* zq, void* stream) {
+    return lookup_common(h, nullptr, packed, B, F, zq, stream);
 }
 
 int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int B, int T, int64_t* idx_host,
@@ -1349,8 +1409,8 @@ int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int
     }
     CK(enc, cudaMemcpyAsync(enc->hx.p, x_host, (size_t)B * T * sizeof(float), cudaMemcpyHostToDevice, s));
     if (adec_encode(enc, enc->hx.p, B, T, enc->hz.p, stream)) return 1;
-    if (adec_quantize(enc, enc->hz.p, B, F, (int64_t*)enc->hidx, stream)) return 1;
-    if (adec_lookup(enc, (const int64_t*)enc->hidx, B, F, enc->hzq.p, stream)) return 1;
+    // quantize + lookup in ONE launch: the RVQ kernel also emits zq (bin/stream.py:224 hand-off without the int64 round trip)
+    if (adec_quantize_ex(enc, enc->hz.p, B, F, (int64_t*)enc->hidx, nullptr, enc->hzq.p, stream)) return 1;
     if (adec_decode(dec, enc->hzq.p, B, F, enc->hy.p, stream)) { enc->err = dec->err; return 1; }
     if (idx_host) CK(enc, cudaMemcpyAsync(idx_host, enc->hidx, nidx * sizeof(long long), cudaMemcpyDeviceToHost, s));
     CK(enc, cudaMemcpyAsync(y_host, enc->hy.p, (size_t)B * F * hop * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1364,13 +1424,6 @@ int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int
         if (hh == dec) break;     // enc == dec
     }
     return 0;
-}
-
-static int index_bits(int n) { int b = 1; while ((1 << b) < n) ++b; return b; }
-
-int adec_packed_frame_bytes(const adec_handle* h) {
-    if (!h || h->cfg.model_type != ADEC_MODEL_SYMAD) return -1;
-    return (h->cfg.codebook_num * index_bits(h->cfg.codebook_size) + 7) / 8;
 }
 
 static int pack_common(adec_handle* h, const char* what, int64_t* idx, int B, int F, uint8_t* packed, void* stream, bool pack) {

@@ -65,17 +65,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag 
     if (mbar_try_wait(b, parity)) return;
 #ifdef ADEC_NO_WATCHDOG
     while (!mbar_try_wait(b, parity)) { }
-    return;
-#endif
+#else
     const long long t0 = clock64();
-    for (unsigned it = 1;; ++it) {
-        if (mbar_try_wait(b, parity)) return;
-        if ((it & 63u) == 0 && clock64() - t0 > ADEC_WATCHDOG_CYCLES) {
+    while (true) {
+        // 64 bare probes (2 instructions each: the polling loop was 16 % of all issued instructions with the clock test inside it)
+#pragma unroll 1
+        for (int it = 0; it < 64; ++it)
+            if (mbar_try_wait(b, parity)) return;
+        if (clock64() - t0 > ADEC_WATCHDOG_CYCLES) {
             printf("adec: mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x);
             __trap();
         }
     }
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -150,6 +153,10 @@ struct ConvArgs {
     // tcgen05 kind::f16 engine (tc_f16.cuh): weights are stored times a power of two; the drain warps multiply the sums by these
     float w_scale, w2_scale;
     int n_wbuf;          // window buffers in shared memory (2..4)
+    // stacked rows: when a stream contributes fewer rows than a 128-row tile, the tiles run over ONE row space in which stream s owns
+    // rows [s * stack_L, (s + 1) * stack_L), stack_L = Tout + (Ktaps - 1) * dil: local rows >= Tout are the receptive-field overlap into
+    // the next stream and are computed but never stored.  0 = one row space per stream (blockIdx-style b dimension).
+    int stack_L, n_streams;
     int* err;            // device flag word: bit 1 = an activation left the fp16-split range (|a| >= 6e4)
 };
 
@@ -523,21 +530,32 @@ struct RvqArgs {
     int B, F, nq;
     const float* embed;    // (nq, D, N) = state-dict `embed` tensors stacked
     const float* e2;       // (nq, N)   ||e||^2 in torch's summation order
-    long long* idx;        // (nq, B, F) flat indices (+ N*i)
+    long long* idx;        // (nq, B, F) flat indices (+ N*i), or nullptr
+    // fused outputs (bin/stream.py:224 hand-off): either may be nullptr
+    unsigned char* packed; // (B*F, bpf) index bitstream, same format as pack_kernel
+    float* zq;             // (B*F, D) = lookup(idx) (vq_module.py:159-161), so that quantize can hand zq straight to the decoder
+    int bits, bpf, n_pass; // bits per index, bytes per packed frame, frame passes per block (frames per block = n_pass * FP)
 };
 
-constexpr int RVQ_FRAMES = 32;    // frames per block: the 256 KB stage codebook is streamed from L2 once per 32 frames
 constexpr int RVQ_THREADS = 256;
 
-template <int D, int NPT>   // codebook size N = RVQ_THREADS * NPT
+// One block quantises n_pass * FP frames through all nq stages.  Thread t owns codewords t, t + 256, ... (NPT of them) for FP frames
+// at a time: FP * NPT independent fused-multiply-add chains over k (ascending, one chain per distance: MKL's sgemm order, which is
+// what makes the indices bit-identical to torch-CPU), codeword elements streamed from L2 (the 256 KB stage table is shared by all
+// blocks), residuals broadcast from shared memory.  The host picks (FP, n_pass) so that the grid is one wave with the least idle
+// tail (adec_quantize), which alone took the 64 x 160-frame case from 0.58 ms (320 blocks of 32 frames = 1.08 waves) to one wave.
+template <int D, int NPT, int FP>   // codebook size N = RVQ_THREADS * NPT
 __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
-    constexpr int N = RVQ_THREADS * NPT, FR = RVQ_FRAMES, NW = RVQ_THREADS / 32;
-    static_assert(D % 32 == 0, "D must be a multiple of 32");
-    __shared__ __align__(16) float r[FR][D];          // residuals
-    __shared__ float x2[FR];
-    __shared__ float wv[FR][NW];
-    __shared__ int wi[FR][NW];
-    __shared__ int best[FR];
+    constexpr int N = RVQ_THREADS * NPT, NW = RVQ_THREADS / 32;
+    static_assert(D % 32 == 0 && FP % 4 == 0, "D must be a multiple of 32, FP of 4");
+    extern __shared__ __align__(16) float rvq_smem[];
+    const int FR = a.n_pass * FP;
+    float* r = rvq_smem;                               // [FR][D] residuals
+    float* zq = r + FR * D;                            // [FR][D] sum of the chosen codewords
+    float* x2 = zq + FR * D;                           // [FR]
+    float* wv = x2 + FR;                               // [FR][NW]
+    int* wi = reinterpret_cast<int*>(wv + FR * NW);    // [FR][NW]
+    int* best = wi + FR * NW;                          // [nq][FR] local indices of every stage (for the packed frame)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const long long nfr = (long long)a.B * a.F;
     const long long f0 = (long long)blockIdx.x * FR;
@@ -549,13 +567,14 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
             const long long bb = fr / a.F, ff = fr - bb * a.F;
             v = a.z[(bb * D + k) * a.F + ff];        // quantizer.py:43 z.transpose(2,1)
         }
-        r[f][k] = v;
+        r[f * D + k] = v;
+        zq[f * D + k] = 0.f;
     }
     __syncthreads();
     for (int st = 0; st < a.nq; ++st) {
         const float* E = a.embed + (long long)st * D * N;
         // x2 = flatten.pow(2).sum(1): 8-lane vectors, 4 interleaved accumulators, sequential horizontal add
-        if (tid < FR) {
+        for (int f = tid; f < FR; f += RVQ_THREADS) {
             float accv[4][8];
 #pragma unroll
             for (int v = 0; v < 4; ++v)
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
             for (int v = 0; v < D / 8; ++v)
 #pragma unroll
                 for (int l = 0; l < 8; ++l) {
-                    const float xv = r[tid][8 * v + l];
+                    const float xv = r[f * D + 8 * v + l];
                     accv[v & 3][l] = __fadd_rn(accv[v & 3][l], __fmul_rn(xv, xv));
                 }
             float s = 0.f;
@@ -574,40 +593,48 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
                 const float t = __fadd_rn(__fadd_rn(__fadd_rn(accv[0][l], accv[1][l]), accv[2][l]), accv[3][l]);
                 s = (l == 0) ? t : __fadd_rn(s, t);
             }
-            x2[tid] = s;
+            x2[f] = s;
         }
-        // dot2[c] = sum_k (2 r_k) * E[k][c], k ascending, one fused multiply-add chain per output (MKL sgemm order).
-        // Frames are processed in two halves of 16 to bound registers; each codebook element is loaded once per half.
         float e2v[NPT];
 #pragma unroll
         for (int m = 0; m < NPT; ++m) e2v[m] = __ldg(a.e2 + (long long)st * N + tid + m * RVQ_THREADS);
         __syncthreads();   // x2 visible
+        // dot2[c] = sum_k (2 r_k) * E[k][c], k ascending, one fused multiply-add chain per output (MKL sgemm order)
 #pragma unroll 1
-        for (int fh = 0; fh < FR; fh += 16) {
-            float acc[16][NPT];
+        for (int fh = 0; fh < FR; fh += FP) {
+            float acc[FP][NPT];
 #pragma unroll
-            for (int f = 0; f < 16; ++f)
+            for (int f = 0; f < FP; ++f)
 #pragma unroll
                 for (int m = 0; m < NPT; ++m) acc[f][m] = 0.f;
+            float e[4][NPT], en[4][NPT];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int m = 0; m < NPT; ++m) e[kk][m] = __ldg(E + (long long)kk * N + tid + m * RVQ_THREADS);
 #pragma unroll 1
             for (int k = 0; k < D; k += 4) {
-                float e[4][NPT];
+                const int kn = k + 4 < D ? k + 4 : k;            // prefetch the next four codeword rows while these are used
 #pragma unroll
                 for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
-                    for (int m = 0; m < NPT; ++m) e[kk][m] = __ldg(E + (long long)(k + kk) * N + tid + m * RVQ_THREADS);
+                    for (int m = 0; m < NPT; ++m) en[kk][m] = __ldg(E + (long long)(kn + kk) * N + tid + m * RVQ_THREADS);
 #pragma unroll
-                for (int f = 0; f < 16; ++f) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(&r[fh + f][k]);
+                for (int f = 0; f < FP; ++f) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(&r[(fh + f) * D + k]);
                     const float rk[4] = {2.0f * r4.x, 2.0f * r4.y, 2.0f * r4.z, 2.0f * r4.w};
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
                         for (int m = 0; m < NPT; ++m) acc[f][m] = fmaf(rk[kk], e[kk][m], acc[f][m]);
                 }
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                    for (int m = 0; m < NPT; ++m) e[kk][m] = en[kk][m];
             }
 #pragma unroll
-            for (int f = 0; f < 16; ++f) {
+            for (int f = 0; f < FP; ++f) {
                 // dist = (x2 - dot2) + e2 ; index = first arg-max of -dist  (vq_module.py:93-98)
                 float bv = 0.f;
                 int bi = 0;
@@ -622,45 +649,70 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
                     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
                 }
-                if (lane == 0) { wv[fh + f][warp] = bv; wi[fh + f][warp] = bi; }
+                if (lane == 0) { wv[(fh + f) * NW + warp] = bv; wi[(fh + f) * NW + warp] = bi; }
             }
         }
         __syncthreads();
-        if (tid < FR) {
-            float bv = wv[tid][0];
-            int bi = wi[tid][0];
+        for (int f = tid; f < FR; f += RVQ_THREADS) {
+            float bv = wv[f * NW];
+            int bi = wi[f * NW];
 #pragma unroll
             for (int w = 1; w < NW; ++w) {
-                const float ov = wv[tid][w];
-                const int oi = wi[tid][w];
+                const float ov = wv[f * NW + w];
+                const int oi = wi[f * NW + w];
                 if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
             }
-            best[tid] = bi;
-            const long long fr = f0 + tid;
-            if (fr < nfr) a.idx[(long long)st * nfr + fr] = (long long)bi + (long long)N * st;   // vq_module.py:145-146
+            best[st * FR + f] = bi;
+            const long long fr = f0 + f;
+            if (a.idx && fr < nfr) a.idx[(long long)st * nfr + fr] = (long long)bi + (long long)N * st;   // vq_module.py:145-146
         }
         __syncthreads();
-        // quantize = x + (e - x); residual -= quantize  (vq_module.py:101-102,143)
+        // quantize = x + (e - x); residual -= quantize  (vq_module.py:101-102,143); zq += e in stage order (vq_module.py:159-161)
         for (int i = tid; i < FR * D; i += RVQ_THREADS) {
             const int f = i / D, k = i - f * D;
-            const float rv = r[f][k];
-            const float q = __ldg(E + (long long)k * N + best[f]);
+            const float rv = r[i];
+            const float q = __ldg(E + (long long)k * N + best[st * FR + f]);
             const float qq = __fadd_rn(rv, __fsub_rn(q, rv));
-            r[f][k] = __fsub_rn(rv, qq);
+            r[i] = __fsub_rn(rv, qq);
+            zq[i] = st == 0 ? q : __fadd_rn(zq[i], q);
         }
         __syncthreads();
     }
+    if (a.zq) {
+        for (int i = tid; i < FR * D / 4; i += RVQ_THREADS) {
+            const long long fr = f0 + (i * 4) / D;
+            if (fr < nfr) *reinterpret_cast<float4*>(a.zq + f0 * D + (long long)i * 4) = *reinterpret_cast<const float4*>(zq + i * 4);
+        }
+    }
+    if (a.packed) {
+        // packed frame: nq local indices of `bits` bits each, stage 0 first, little-endian bit order (same bytes as pack_kernel)
+        for (int f = tid; f < FR; f += RVQ_THREADS) {
+            const long long fr = f0 + f;
+            if (fr >= nfr) continue;
+            unsigned char* o = a.packed + fr * a.bpf;
+            unsigned long long accb = 0;
+            int nb = 0, ob = 0;
+            for (int i = 0; i < a.nq; ++i) {
+                accb |= (unsigned long long)best[i * FR + f] << nb;
+                nb += a.bits;
+                while (nb >= 8) { o[ob++] = (unsigned char)(accb & 0xffu); accb >>= 8; nb -= 8; }
+            }
+            if (nb > 0) o[ob++] = (unsigned char)(accb & 0xffu);
+        }
+    }
 }
 
-// codebook lookup (vq_module.py:159-161): zq[b][f][:] = sum_i codebook[idx[i][b][f]][:], i ascending
+// codebook lookup (vq_module.py:159-161): zq[b][f][:] = sum_i codebook[idx[i][b][f]][:], i ascending.  The indices come either as the
+// int64 (nq, B*F) tensor of the reference or straight from the packed bitstream (unpack fused into the lookup).
 struct LookupArgs {
-    const long long* idx;   // (nq, B*F)
+    const long long* idx;   // (nq, B*F) or nullptr
+    const unsigned char* packed;   // (B*F, bpf) or nullptr
     long long nfr;
-    int nq, D;
+    int nq, D, N, bits, bpf;
     const float* codebook;  // (nq*N, D)
     long long n_rows;       // nq*N (bounds check)
     float* zq;              // (B*F, D)
-    int* err;               // set to 1 on an out-of-range index
+    int* err;               // bit 0 set on an out-of-range index
 };
 
 __global__ void __launch_bounds__(256) lookup_kernel(const LookupArgs a) {
@@ -670,9 +722,21 @@ __global__ void __launch_bounds__(256) lookup_kernel(const LookupArgs a) {
     const long long fr = gid / vpf;
     const int k4 = (int)(gid - fr * vpf) * 4;
     float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const unsigned char* in = a.packed ? a.packed + fr * a.bpf : nullptr;
+    const unsigned long long mask = (1ull << a.bits) - 1ull;
+    unsigned long long accb = 0;
+    int nb = 0, ib = 0;
     for (int i = 0; i < a.nq; ++i) {
-        const long long row = a.idx[(long long)i * a.nfr + fr];
-        if (row < 0 || row >= a.n_rows) { *a.err = 1; continue; }
+        long long row;
+        if (in) {
+            while (nb < a.bits) { accb |= (unsigned long long)in[ib++] << nb; nb += 8; }
+            const long long v = (long long)(accb & mask);
+            accb >>= a.bits; nb -= a.bits;
+            row = v < a.N ? v + (long long)i * a.N : -1;
+        } else {
+            row = a.idx[(long long)i * a.nfr + fr];
+        }
+        if (row < 0 || row >= a.n_rows) { atomicOr(a.err, 1); continue; }
         const float4 v = __ldg(reinterpret_cast<const float4*>(a.codebook + row * a.D + k4));
         if (i == 0) s = v;
         else { s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w); }
@@ -699,7 +763,7 @@ __global__ void __launch_bounds__(256) pack_kernel(const PackArgs a) {
     int nb = 0, ob = 0;
     for (int i = 0; i < a.nq; ++i) {
         long long v = a.idx[(long long)i * a.nfr + fr] - (long long)i * a.N;
-        if (v < 0 || v >= a.N) { *a.err = 1; v = 0; }
+        if (v < 0 || v >= a.N) { atomicOr(a.err, 1); v = 0; }
         acc |= (unsigned long long)v << nb;
         nb += a.bits;
         while (nb >= 8) { o[ob++] = (unsigned char)(acc & 0xffu); acc >>= 8; nb -= 8; }
@@ -718,7 +782,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const PackArgs a) {
         while (nb < a.bits) { acc |= (unsigned long long)in[ib++] << nb; nb += 8; }
         long long v = (long long)(acc & mask);
         acc >>= a.bits; nb -= a.bits;
-        if (v >= a.N) { *a.err = 1; v = 0; }
+        if (v >= a.N) { atomicOr(a.err, 1); v = 0; }
         a.idx[(long long)i * a.nfr + fr] = v + (long long)i * a.N;
     }
 }

@@ -98,6 +98,32 @@ __device__ __forceinline__ void split_store(unsigned char* hi, unsigned char* lo
     }
 }
 
+// Persistent-tile iterator: tile = xt + n_x * (y + n_y * b) advances by gridDim.x per step.  Decoding it with / and % costs ~100
+// instructions per tile in EVERY thread (12 % of all instructions of the C = 32 unit in the first ncu capture); the increments below
+// are carried additions.
+struct TileIter {
+    int tile, xt, y, b, sx, sy, sb, nx, ny;
+    __device__ __forceinline__ TileIter(int first, int step, int n_x, int n_y) {
+        nx = n_x; ny = n_y; tile = first;
+        xt = first % n_x;
+        const int q = first / n_x;
+        y = q % n_y; b = q / n_y;
+        sx = step % n_x;
+        const int sq = step / n_x;
+        sy = sq % n_y; sb = sq / n_y;
+    }
+    __device__ __forceinline__ void next(int step) {
+        tile += step;
+        xt += sx;
+        const int cx = xt >= nx ? 1 : 0;
+        xt -= cx ? nx : 0;
+        y += sy + cx;
+        const int cy = y >= ny ? 1 : 0;
+        y -= cy ? ny : 0;
+        b += sb + cy;
+    }
+};
+
 __device__ __forceinline__ float4 norm4(float4 x, const float* mean, const float* scale) {
     const float4 mu = *reinterpret_cast<const float4*>(mean);
     const float4 sc = *reinterpret_cast<const float4*>(scale);
@@ -180,17 +206,19 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
             };
             const unsigned char* w1 = reinterpret_cast<const unsigned char*>(a.w);
             const unsigned char* w2 = reinterpret_cast<const unsigned char*>(a.w2);
-            auto w1_of = [&](int tile) { return w1 + (long long)((tile / n_xtiles) % n_ytiles) * a.w_tile_floats * 4; };
+            auto w1_of = [&](int y) { return w1 + (long long)y * a.w_tile_floats * 4; };
+            TileIter it(blockIdx.x, gridDim.x, n_xtiles, n_ytiles);
             if (PIPE) {
                 // same order as the MMA warps: G1(t0), then per tile { G1(next), G2(this) }
-                if ((int)blockIdx.x < n_tiles) stream(w1_of(blockIdx.x), a.n_pieces, a.Ktaps);
-                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                    if (tile + (int)gridDim.x < n_tiles) stream(w1_of(tile + gridDim.x), a.n_pieces, a.Ktaps);
+                if (it.tile < n_tiles) stream(w1_of(it.y), a.n_pieces, a.Ktaps);
+                while (it.tile < n_tiles) {
+                    it.next(gridDim.x);
+                    if (it.tile < n_tiles) stream(w1_of(it.y), a.n_pieces, a.Ktaps);
                     stream(w2, n_g2, 1);
                 }
             } else {
-                for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                    stream(w1_of(tile), a.n_pieces, a.Ktaps);
+                for (; it.tile < n_tiles; it.next(gridDim.x)) {
+                    stream(w1_of(it.y), a.n_pieces, a.Ktaps);
                     if (FUSE) stream(w2, n_g2, 1);
                 }
             }
@@ -198,7 +226,8 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
     } else if (warp >= 1 && warp <= NW) {
         // ------------------------------------------------ MMA issuers (groups round robin)
         const int mw = warp - 1;
-        int c = 0, wp = 0, mp = 0;
+        int c = 0, mp = 0;
+        int wb = 0, wround = 0;                                   // window piece counter wp = wround * n_wbuf + wb
         const uint32_t b_lbo = (uint32_t)NT * 16u;
         const uint32_t wbuf0_u = smem_u32(wbuf0), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
         // one group: ntaps (1 or 2) taps of one 32-channel piece; tap t reads window rows shifted by row_off + t * tap_step bytes
@@ -241,9 +270,10 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
         const uint32_t lbo1 = (uint32_t)wrp * 16u, lbo2 = (uint32_t)MIDP * 16u;
         const uint32_t tap_step = (uint32_t)a.dil * 16u;
         auto gemm1 = [&]() {        // one tile's conv over its window pieces
-            for (int p = 0; p < a.n_pieces; ++p, ++wp) {
-                const int buf = wp % a.n_wbuf;
-                mbar_wait(&w_full[buf], (wp / a.n_wbuf) & 1, 200);
+            for (int p = 0; p < a.n_pieces; ++p) {
+                const int buf = wb;
+                mbar_wait(&w_full[buf], wround & 1, 200);
+                if (++wb == a.n_wbuf) { wb = 0; ++wround; }
                 const uint32_t a_hi = wbuf0_u + (uint32_t)buf * (uint32_t)win_b;
                 const uint32_t a_lo = a_hi + (uint32_t)KB * lbo1;
                 for (int t0 = 0; t0 < a.Ktaps; t0 += 2, ++c)
@@ -280,18 +310,23 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
         // The loads of a piece are issued BEFORE the wait for a free window buffer, so global latency overlaps the MMAs that still read
         // the buffer; a.n_wbuf (2..4) buffers let the producers run several pieces ahead.
         const int pt = tid - 128;
-        int wp = 0;
+        int wb = 0, wround = 0;                    // window piece counter wp = wround * n_wbuf + wb
         constexpr int RPP = NPROD / KB;            // window rows per pass
         constexpr int UNR = NPROD == 128 ? 5 : 3;  // rows in flight per thread (2 x 128-bit loads each): one pass covers 160 / 192 rows
         const int c8 = pt & (KB - 1), m0 = pt >> 2;
         const bool halves = a.RG > 1 && a.Cin < 8; // a 4-channel strided conv: the two halves of a block are different x~ rows
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
-            const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+        for (TileIter it(blockIdx.x, gridDim.x, n_xtiles, n_ytiles); it.tile < n_tiles; it.next(gridDim.x)) {
+            const int xt = it.xt, y = it.y, b = it.b;
+            int g = 0, co_tile = y;
+            if (a.n_co_tiles != n_ytiles) { g = y / a.n_co_tiles; co_tile = y - g * a.n_co_tiles; }
+            const int j0 = xt * TT;
             const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
             const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
-            for (int p = 0; p < a.n_pieces; ++p, ++wp) {
-                const int buf = wp % a.n_wbuf;
+            for (int p = 0; p < a.n_pieces; ++p) {
+                const int buf = wb;
+                const uint32_t wpar = (uint32_t)(wround - 1) & 1u;
+                bool waited = wround == 0;
+                if (++wb == a.n_wbuf) { wb = 0; ++wround; }
                 unsigned char* hi = wbuf0 + (size_t)buf * win_b + (size_t)c8 * wrp * 16;
                 unsigned char* lo = hi + (size_t)KB * wrp * 16;
                 const int q = p * CP + c8 * 8;
@@ -299,8 +334,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
                 if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
                 const long long i_first = (long long)j0 * a.RG + r;
                 const long long i_last = (long long)(j0 + wrows - 1) * a.RG + r;
-                bool waited = wp < a.n_wbuf;
-                if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM && !halves) {
+                if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM && !halves && !a.stack_L) {
                     // interior piece: every row comes from the chunk
                     const float* xp = xg + ci + (i_first - a.P + (long long)m0 * a.RG) * a.ldx;
                     const long long xstep = (long long)RPP * a.RG * a.ldx;
@@ -312,7 +346,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
                                 u[k] = __ldg(reinterpret_cast<const float4*>(xp + k * xstep));
                                 v[k] = __ldg(reinterpret_cast<const float4*>(xp + k * xstep) + 1);
                             }
-                        if (!waited) { mbar_wait(&w_empty[buf], ((wp / a.n_wbuf) - 1) & 1, 500); waited = true; }
+                        if (!waited) { mbar_wait(&w_empty[buf], wpar, 500); waited = true; }
 #pragma unroll
                         for (int k = 0; k < UNR; ++k) {
                             const int m = mb + k * RPP;
@@ -330,21 +364,35 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
                             const int m = mb + k * RPP;
                             u[k] = v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (m < wrows) {
+                                // stacked rows: window row j0 + m of the stack is local row `ml` of stream `sm`
+                                int ml = j0 + m;
+                                const float* xs = xg;
+                                const float* ss = sg;
+                                bool live = true;
+                                if (a.stack_L) {
+                                    const int sm = ml / a.stack_L;
+                                    ml -= sm * a.stack_L;
+                                    live = sm < a.n_streams;
+                                    xs = xg + (long long)sm * a.x_bs;
+                                    ss = sg + (long long)sm * a.P * a.st_ld;
+                                }
 #pragma unroll
                                 for (int hf = 0; hf < 2; ++hf) {
                                     int rr = r, cc = ci + 4 * hf;
                                     if (halves) { rr = (q + 4 * hf) >> a.lgCin; cc = (q + 4 * hf) & (a.Cin - 1); if (hf) ci2 = cc; }
-                                    const long long i = (long long)(j0 + m) * a.RG + rr;
+                                    const long long i = (long long)ml * a.RG + rr;
                                     long long ti = i - a.P;
                                     if (a.hist_rep && ti < 0) ti = 0;              // non-streaming transposed conv: replicate the first input row
                                     float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                                    if (ti < 0) w4 = __ldg(reinterpret_cast<const float4*>(sg + i * a.st_ld + cc));
-                                    else if (ti < a.T) { w4 = __ldg(reinterpret_cast<const float4*>(xg + ti * a.ldx + cc)); act |= 1u << (2 * k + hf); }
+                                    if (live) {
+                                        if (ti < 0) w4 = __ldg(reinterpret_cast<const float4*>(ss + i * a.st_ld + cc));
+                                        else if (ti < a.T) { w4 = __ldg(reinterpret_cast<const float4*>(xs + ti * a.ldx + cc)); act |= 1u << (2 * k + hf); }
+                                    }
                                     if (hf) v[k] = w4; else u[k] = w4;
                                 }
                             }
                         }
-                        if (!waited) { mbar_wait(&w_empty[buf], ((wp / a.n_wbuf) - 1) & 1, 500); waited = true; }
+                        if (!waited) { mbar_wait(&w_empty[buf], wpar, 500); waited = true; }
 #pragma unroll
                         for (int k = 0; k < UNR; ++k) {
                             const int m = mb + k * RPP;
@@ -360,23 +408,38 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
                 fence_async_smem();
                 mbar_arrive(&w_full[buf]);
             }
-            // ---- new causal state (conv_layer.py:155)
-            if (xt == (a.Tout - 1) / TT && co_tile == 0 && g < a.st_groups && a.P > 0) {
-                float* so = a.st_out + (long long)b * a.P * a.st_ld + g * a.st_goff;
-                const int nvec = a.P * (a.Cin / 4);
-                for (int idx = pt; idx < nvec; idx += NPROD) {
-                    const int r = idx / (a.Cin / 4);
-                    const int cc = (idx - r * (a.Cin / 4)) * 4;
-                    const long long i = (long long)a.T + r;
-                    float4 w4;
-                    if (i < a.P) {
-                        w4 = *reinterpret_cast<const float4*>(sg + i * a.st_ld + cc);
-                    } else {
-                        w4 = __ldg(reinterpret_cast<const float4*>(xg + (i - a.P) * a.ldx + cc));
-                        if (PRE == ACT_NORM) w4 = norm4(w4, a.mean + cc, a.scale + cc);
-                        else w4 = apply_act_t<PRE>(w4, a.slope);
+            // ---- new causal state (conv_layer.py:155): written by the CTA whose tile holds the stream's last output row
+            if (co_tile == 0 && g < a.st_groups && a.P > 0) {
+                int s_lo = b, s_hi = b - 1;
+                if (a.stack_L) {
+                    // streams whose last valid row sm * L + Tout - 1 lies in [j0, j0 + TT)
+                    s_lo = (j0 - (a.Tout - 1) + a.stack_L - 1) / a.stack_L;
+                    if (j0 < a.Tout - 1) s_lo = 0;
+                    s_hi = (j0 + TT - 1 - (a.Tout - 1)) / a.stack_L;
+                    if (j0 + TT - 1 < a.Tout - 1) s_hi = -1;
+                    if (s_hi > a.n_streams - 1) s_hi = a.n_streams - 1;
+                } else if (xt == (a.Tout - 1) / TT) {
+                    s_hi = b;
+                }
+                for (int sm = s_lo; sm <= s_hi; ++sm) {
+                    const float* xs = a.x + (long long)sm * a.x_bs + g * a.x_goff;
+                    const float* ss = a.st_in + (long long)sm * a.P * a.st_ld + g * a.st_goff;
+                    float* so = a.st_out + (long long)sm * a.P * a.st_ld + g * a.st_goff;
+                    const int nvec = a.P * (a.Cin / 4);
+                    for (int idx = pt; idx < nvec; idx += NPROD) {
+                        const int r = idx / (a.Cin / 4);
+                        const int cc = (idx - r * (a.Cin / 4)) * 4;
+                        const long long i = (long long)a.T + r;
+                        float4 w4;
+                        if (i < a.P) {
+                            w4 = *reinterpret_cast<const float4*>(ss + i * a.st_ld + cc);
+                        } else {
+                            w4 = __ldg(reinterpret_cast<const float4*>(xs + (i - a.P) * a.ldx + cc));
+                            if (PRE == ACT_NORM) w4 = norm4(w4, a.mean + cc, a.scale + cc);
+                            else w4 = apply_act_t<PRE>(w4, a.slope);
+                        }
+                        *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + cc) = w4;
                     }
-                    *reinterpret_cast<float4*>(so + (long long)r * a.st_ld + cc) = w4;
                 }
             }
         }
@@ -427,9 +490,15 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
             for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
             drain(racc, n_g1);                                // conv of the first tile
         }
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const int xt = tile % n_xtiles, y = (tile / n_xtiles) % n_ytiles, b = tile / (n_xtiles * n_ytiles);
-            const int j0 = xt * TT, g = y / a.n_co_tiles, co_tile = y - g * a.n_co_tiles;
+        for (TileIter it(blockIdx.x, gridDim.x, n_xtiles, n_ytiles); it.tile < n_tiles; it.next(gridDim.x)) {
+            const int tile = it.tile, xt = it.xt, y = it.y, b = it.b;
+            int g = 0, co_tile = y;
+            if (a.n_co_tiles != n_ytiles) { g = y / a.n_co_tiles; co_tile = y - g * a.n_co_tiles; }
+            const int j0 = xt * TT;
+            // this thread's output row: (stream bo, time t); stacked launches carry several streams per tile and skip the rows between them
+            int bo = b, t = j0 + row;
+            if (a.stack_L) { bo = t / a.stack_L; t -= bo * a.stack_L; }
+            const bool row_ok = t < a.Tout && bo < a.n_streams;
             if (!PIPE) {
 #pragma unroll
                 for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
@@ -468,12 +537,12 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
                 mq += NT / CP;
 #pragma unroll
                 for (int i = 0; i < NCOL; ++i) racc[i] = 0.f;
-                if (PREFETCH_RES && a.res && j0 + row < a.Tout) {
+                if (PREFETCH_RES && a.res && row_ok) {
                     // the skip tensor's rows are known now: fetch them while the MMAs run
 #pragma unroll
                     for (int pl = 0; pl < PPG; ++pl) {
                         const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
-                        const float* rp = a.res + (long long)b * a.res_bs + (long long)(j0 + row) * a.ldr + g * a.r_goff + co_l;
+                        const float* rp = a.res + (long long)bo * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
 #pragma unroll
                         for (int i = 0; i < UC / 4; ++i) rpre[pl][i] = __ldg(reinterpret_cast<const float4*>(rp) + i);
                     }
@@ -491,8 +560,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
             float* const outv = PIPE ? oacc : racc;
             const float oscale = FUSE ? a.w2_scale : a.w_scale;
             // ---- epilogue: row `row` of the tile, this group's PPG pieces of 32 channels
-            const int t = j0 + row;
-            if (t < a.Tout) {
+            if (row_ok) {
 #pragma unroll
                 for (int pl = 0; pl < PPG; ++pl) {
                     const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
@@ -508,7 +576,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
                         }
                     }
                     if (a.res) {
-                        const float* rp = a.res + (long long)b * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
+                        const float* rp = a.res + (long long)bo * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
                         float4 r4[UC / 4];
 #pragma unroll
                         for (int i = 0; i < UC / 4; ++i)
@@ -522,11 +590,11 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
 #pragma unroll
                     for (int i = 0; i < UC; ++i) vmax = fmaxf(vmax, fabsf(v[i]));
                     if (a.out_nct) {
-                        float* yp = a.y + (long long)b * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
+                        float* yp = a.y + (long long)bo * a.y_bs + (long long)(g * a.y_goff + co_l) * a.Tout + t;
 #pragma unroll
                         for (int i = 0; i < UC; ++i) yp[(long long)i * a.Tout] = v[i];
                     } else {
-                        float* yp = a.y + (long long)b * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
+                        float* yp = a.y + (long long)bo * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
 #pragma unroll
                         for (int i = 0; i < UC / 4; ++i)
                             *(reinterpret_cast<float4*>(yp) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);

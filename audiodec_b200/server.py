@@ -125,12 +125,19 @@ class MultiStreamCodecServer:
         live = sum(t is not None for t in stamps)
         with torch.no_grad():
             x = x_host.to(dev, non_blocking=True)
-            idx = self.tx_encoder.quantize(self.tx_encoder.encode(x))          # utils/audiodec.py:100-102
-            if self.wire:
-                packed = self.tx_encoder.pack(idx)
+            z = self.tx_encoder.encode(x)                                       # utils/audiodec.py:100-102
+            if self.wire and hasattr(self.tx_encoder, "quantize_fused") and hasattr(self.rx_encoder, "lookup_packed"):
+                # the RVQ kernel writes the bitstream itself; the receiver looks the codewords up straight from the packed bytes
+                _, packed, _ = self.tx_encoder.quantize_fused(z, want_idx=False, want_packed=True, want_zq=False)
                 self.wire_bytes += packed.numel()
-                idx = self.rx_encoder.unpack(packed)
-            y = self.decoder.decode(self.rx_encoder.lookup(idx))               # utils/audiodec.py:104-106
+                zq = self.rx_encoder.lookup_packed(packed)
+            elif self.wire:
+                packed = self.tx_encoder.pack(self.tx_encoder.quantize(z))
+                self.wire_bytes += packed.numel()
+                zq = self.rx_encoder.lookup(self.rx_encoder.unpack(packed))
+            else:
+                zq = self.rx_encoder.lookup(self.tx_encoder.quantize(z))
+            y = self.decoder.decode(zq)                                         # utils/audiodec.py:104-106
             y_host = y.detach().to("cpu")                                       # synchronises with the launches above
         now = self._clock()
         y_np = y_host.numpy().reshape(self.n_streams, -1)

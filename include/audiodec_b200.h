@@ -97,6 +97,10 @@ int adec_reset(adec_handle *h, void *stream);
 int adec_encode(adec_handle *h, const float *x, int B, int T, float *z, void *stream);
 /* StreamGenerator.quantize (AudioDec.py:237-239): z (B,code_dim,F) -> idx (Nq,B,F) int64. Stateless. */
 int adec_quantize(adec_handle *h, const float *z, int B, int F, int64_t *idx, void *stream);
+/* Fused form of the quantize -> [pack] -> lookup hand-off (bin/stream.py:224 ships the int64 tensor through a queue): ONE launch
+ * writes any of idx (Nq,B,F) int64, packed (B,F,adec_packed_frame_bytes) uint8 and zq (B,F,code_dim) = lookup(idx); pass NULL for
+ * outputs that are not wanted (at least one must be given).  Same arithmetic, bit-identical to quantize + pack + lookup. */
+int adec_quantize_ex(adec_handle *h, const float *z, int B, int F, int64_t *idx, uint8_t *packed, float *zq, void *stream);
 /* StreamGenerator.lookup (AudioDec.py:242-243): idx (Nq,B,F) -> zq (B,F,code_dim). Stateless. */
 int adec_lookup(adec_handle *h, const int64_t *idx, int B, int F, float *zq, void *stream);
 /* StreamGenerator.decode (AudioDec.py:246-247 / HiFiGAN.py:268-273): zq (B,F,code_dim) -> y (B,1,F*hop). */
@@ -131,6 +135,8 @@ int adec_codec_host(adec_handle *enc, adec_handle *dec, const float *x_host, int
 int adec_packed_frame_bytes(const adec_handle *h);       /* -1 if h is not a symAD handle */
 int adec_pack_indices(adec_handle *h, const int64_t *idx, int B, int F, uint8_t *packed, void *stream);
 int adec_unpack_indices(adec_handle *h, const uint8_t *packed, int B, int F, int64_t *idx, void *stream);
+/* lookup straight from the packed bitstream (unpack fused into lookup): packed (B,F,bytes) -> zq (B,F,code_dim) */
+int adec_lookup_packed(adec_handle *h, const uint8_t *packed, int B, int F, float *zq, void *stream);
 /* synchronises `stream`, then returns and clears the handle's device-side flag: 1 if lookup / pack / unpack met an
  * out-of-range index since the last call (the reference's F.embedding would have raised, vq_module.py:160), -1 on error */
 int adec_index_error(adec_handle *h, void *stream);

@@ -128,6 +128,21 @@ class SymADOracle:
                 assert v.shape[0] == 1, "can only expand batch-1 state"
                 self.state[k] = v.repeat(b, 1, 1)
 
+    def to(self, device):
+        """Move weights and causal state (bench.py's informational eager-GPU baseline: the same torch ops on a CUDA device)."""
+        mv = lambda t: t.to(device) if torch.is_tensor(t) else t
+        for name in ("sd", "w", "state"):
+            d = getattr(self, name, None)
+            if d is not None:
+                for k in list(d):
+                    d[k] = mv(d[k])
+        for name in ("mean", "scale", "codebook"):
+            if getattr(self, name, None) is not None:
+                setattr(self, name, mv(getattr(self, name)))
+        if getattr(self, "embeds", None) is not None:
+            self.embeds = [mv(e) for e in self.embeds]
+        return self
+
     def _ensure_batch(self, b):
         any_state = next(iter(self.state.values()))
         if any_state.shape[0] != b:
@@ -253,6 +268,21 @@ class HiFiGANOracle:
 
     def initial_decoder(self, c):                        # HiFiGAN.py:264-265
         self.decode(c)
+
+    def to(self, device):
+        """Move weights and causal state (bench.py's informational eager-GPU baseline: the same torch ops on a CUDA device)."""
+        mv = lambda t: t.to(device) if torch.is_tensor(t) else t
+        for name in ("sd", "w", "state"):
+            d = getattr(self, name, None)
+            if d is not None:
+                for k in list(d):
+                    d[k] = mv(d[k])
+        for name in ("mean", "scale", "codebook"):
+            if getattr(self, name, None) is not None:
+                setattr(self, name, mv(getattr(self, name)))
+        if getattr(self, "embeds", None) is not None:
+            self.embeds = [mv(e) for e in self.embeds]
+        return self
 
     def _conv(self, name, x, dilation=1, groups=1):
         y, self.state[name] = causal_conv1d_infer(

@@ -103,6 +103,40 @@ def test_v1_vocoder_golden(golden_dir, symad_sd, hifigan_sd, conv_path):
     np.testing.assert_allclose(torch.cat(ys, -1).numpy(), gs["y"], atol=WAVE_TOL)
 
 
+def test_v1_vocoder_bf16_mode(golden_dir, symad_sd, hifigan_sd):
+    """BASELINE configs[2]: HiFi-GAN v1 vocoder with bf16 conv operands (`decoder.to(torch.bfloat16)`), encoder / RVQ fp32-grade.
+    The reference defines no reduced-precision tolerance, so it is derived from the reference itself (tests/golden/make_golden_bf16.py):
+    its own bf16 vocoder is 1.70e-2 max-abs / 36.9 dB SNR away from its fp32 output on this clip.  Bar: indices bit-identical (the
+    encoder side is untouched), waveform within 2e-2 max-abs and >= 35 dB SNR of the fp32 reference - i.e. no worse than the
+    reference's own bf16 path - and within 4e-2 of the reference's bf16 output."""
+    from audiodec_b200.codec import HiFiGANStreamGenerator, SymADStreamGenerator
+    g = np.load(os.path.join(golden_dir, "v1_bf16.npz"))
+    dev = torch.device("cuda:0")
+    enc = []
+    for _ in range(2):
+        e = SymADStreamGenerator(**S.SYMAD_PARAMS)
+        e.load_state_dict(symad_sd)
+        enc.append(e.eval().to(dev))
+    d = HiFiGANStreamGenerator(**S.HIFIGAN_V1_PARAMS)
+    d.load_state_dict(hifigan_sd)
+    d = d.to(torch.bfloat16).eval().to(dev)
+    tx, rx = enc
+    tx.initial_encoder(8192, dev)
+    d.initial_decoder(rx.initial_encoder(8192, dev))
+    z, idx, zq, y = _run(tx, rx, d, torch.from_numpy(g["x"]))
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    y32, y16 = torch.from_numpy(g["y_fp32"]), torch.from_numpy(g["y_bf16"])
+    err = (y - y32).abs().max().item()
+    snr = (10 * torch.log10(y32.pow(2).mean() / (y - y32).pow(2).mean())).item()
+    ref_err = (y16 - y32).abs().max().item()
+    print(f"[parity] bf16 vocoder: max-abs vs fp32 reference {err:.3e} (reference's own bf16: {ref_err:.3e}), SNR {snr:.1f} dB, "
+          f"vs reference bf16 {(y - y16).abs().max().item():.3e}")
+    assert err <= 2e-2 and snr >= 35.0
+    assert (y - y16).abs().max().item() <= 4e-2
+    with pytest.raises(NotImplementedError):
+        SymADStreamGenerator(**S.SYMAD_PARAMS).to(torch.bfloat16)          # the encoder side has no reduced-precision mode
+
+
 def test_quantize_bit_exact_vs_oracle_same_z(symad_sd):
     """Given the SAME z, the CUDA RVQ reproduces torch-CPU's decisions: compare 64x160 frames x 8 stages."""
     from oracle import audiodec_oracle as O
@@ -308,6 +342,29 @@ def test_index_bitstream_matches_oracle_and_round_trips(symad_sd):
     bad[3, 1, 2] = 8 * 1024 + 1
     rx.lookup(bad)
     assert rx.index_error() and not rx.index_error()
+
+
+@pytest.mark.parametrize("B,F", [(3, 37), (1, 5), (64, 160), (256, 5)])
+def test_fused_quantize_pack_lookup_is_bit_identical(symad_sd, B, F):
+    """the RVQ kernel's fused outputs (indices, packed frames, zq) equal quantize -> pack -> lookup, and
+    lookup_packed equals lookup(unpack(.)), bit for bit - over ragged, single-stream, benchmark-size and 256-stream shapes (each
+    picks a different frames-per-pass / passes-per-block launch)."""
+    tx, rx, dec, _ = _codec(symad_sd)
+    torch.manual_seed(100 + B)
+    z = (0.6 * torch.randn(B, 64, F)).cuda()
+    idx = tx.quantize(z)
+    packed = tx.pack(idx)
+    zq = rx.lookup(idx)
+    fi, fp, fz = tx.quantize_fused(z, want_idx=True, want_packed=True, want_zq=True)
+    assert torch.equal(fi, idx) and torch.equal(fp, packed) and torch.equal(fz, zq)
+    assert torch.equal(rx.lookup_packed(packed), zq)
+    only = tx.quantize_fused(z, want_idx=False, want_packed=True, want_zq=False)
+    assert only[0] is None and only[2] is None and torch.equal(only[1], packed)
+    assert not tx.index_error() and not rx.index_error()
+    bad = packed.clone().reshape(-1, packed.shape[-1])
+    bad[0, 0] = 0xFF; bad[0, 1] = 0xFF                              # 10-bit code 1023 is valid; force stage 1 out of range is impossible
+    rx.lookup_packed(bad.reshape(packed.shape))                     # (every 10-bit value < 1024): the flag must stay clear
+    assert not rx.index_error()
 
 
 def test_index_bitstream_16_codebooks():

@@ -150,7 +150,7 @@ cudaError_t launch_tcf(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tile
         configured[dev] = true;
     }
     if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
-    kern<<<n_ctas, TcfCfg<NT, PREC>::THREADS, smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
+    kern<<<n_ctas, TcfCfg<NT, PREC>::threads(F), smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
     return cudaGetLastError();
 }
 typedef size_t (*TcfSmemFn)(int, bool);
@@ -245,6 +245,8 @@ struct adec_handle {
     bool use_tc = true;           // any tensor-core engine
     bool bf16 = false;            // cfg.compute_dtype == 1: bf16 operands (HiFi-GAN vocoder, f16 engine only)
     bool stack_rows = true;       // ADEC_STACK_ROWS=0: never stack several streams' rows into one tile (A/B)
+    unsigned long long* d_ktrace = nullptr;   // ADEC_KTRACE=1: per-launch {start ns, end ns, SM cycles} records (diagnostics)
+    int ktrace_n = 0;
     int n_sms = 148;
     DevBuf ws[3];
     std::vector<void*> owned;     // device allocations freed in destroy
@@ -709,6 +711,7 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.mid_act = op.mid_act;
             a.hist_rep = (rc.offline && op.up > 1) ? 1 : 0;
             a.w_scale = op.w_scale; a.w2_scale = op.w2_scale; a.err = h->d_err;
+            if (h->d_ktrace && h->ktrace_n < 4096) a.dbg = h->d_ktrace + 3 * (size_t)(h->ktrace_n++);
             if (op.tcf || op.tc) {
                 // persistent tensor-core kernels: one CTA per SM loops over (time tile, channel tile, stream) tiles
                 const int wrows = TC_TT + (op.Ktaps - 1) * op.dil;
@@ -719,7 +722,8 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
                     // fill the 128-row tiles across streams when that needs fewer tiles (short chunks: 256 streams x 5..25 rows per layer)
                     const long long L = (long long)Tout + (long long)(op.Ktaps - 1) * op.dil;
                     const long long stacked = (rc.B * L + TC_TT - 1) / TC_TT;
-                    if (stacked < (long long)grid.x * rc.B && rc.B * L < (1ll << 30)) {
+                    // (stacked tiles take the per-row edge path in the producers: only worth it when at least a quarter of the tiles go away)
+                    if (stacked * 4 <= (long long)grid.x * rc.B * 3 && rc.B * L < (1ll << 30)) {
                         a.stack_L = (int)L;
                         grid = dim3((unsigned)stacked, grid.y, 1);
                     }
@@ -1137,6 +1141,9 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     }
     h->use_tc = h->engine != 0;
     if (const char* sr = getenv("ADEC_STACK_ROWS")) h->stack_rows = atoi(sr) != 0;
+    if (const char* kt = getenv("ADEC_KTRACE")) {
+        if (atoi(kt)) { DeviceGuard dgk(device); cudaMalloc((void**)&h->d_ktrace, 4096 * 3 * sizeof(unsigned long long)); }
+    }
     h->bf16 = cfg->compute_dtype == 1;
     if (cfg->compute_dtype != 0 && cfg->compute_dtype != 1) { g_create_error = "compute_dtype must be 0 (fp32) or 1 (bf16)"; delete h; return 1; }
     if (h->bf16 && (cfg->model_type != ADEC_MODEL_HIFIGAN || h->engine != 2)) {
@@ -1168,6 +1175,7 @@ void adec_destroy(adec_handle* h) {
     for (DevBuf* b : {&h->hx, &h->hz, &h->hzq, &h->hy}) if (b->p) cudaFree(b->p);
     if (h->hidx) cudaFree(h->hidx);
     if (h->d_err) cudaFree(h->d_err);
+    if (h->d_ktrace) cudaFree(h->d_ktrace);
     delete h;
 }
 
@@ -1472,6 +1480,15 @@ int adec_index_error(adec_handle* h, void* stream) { return read_flag(h, stream,
 int adec_range_error(adec_handle* h, void* stream) { return read_flag(h, stream, 2); }
 
 int64_t adec_launch_count(const adec_handle* h) { return h ? h->launches : 0; }
+
+int adec_ktrace(adec_handle* h, unsigned long long* out, int max_records) {
+    if (!h || !h->d_ktrace || !out) return -1;
+    DeviceGuard dg(h->device);
+    const int n = std::min(h->ktrace_n, max_records);
+    if (cudaDeviceSynchronize() != cudaSuccess || cudaMemcpy(out, h->d_ktrace, (size_t)n * 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    h->ktrace_n = 0;
+    return n;
+}
 
 int adec_probe_mma(int device, int kind, int NT, int n_groups, double* tflops, double* ms) {
     if (!tflops || (kind != 0 && kind != 1) || NT < 16 || NT > 256 || NT % 16 || n_groups < 1) { g_create_error = "probe_mma: bad argument"; return 1; }

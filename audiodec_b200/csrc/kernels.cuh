@@ -70,8 +70,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag 
     while (true) {
         // 64 bare probes (2 instructions each: the polling loop was 16 % of all issued instructions with the clock test inside it)
 #pragma unroll 1
-        for (int it = 0; it < 64; ++it)
+        for (int it = 0; it < 64; ++it) {
             if (mbar_try_wait(b, parity)) return;
+#ifdef ADEC_WAIT_SLEEP
+            if (tag != 200 && tag != 250 && tag != 300 && tag != 400) __nanosleep(ADEC_WAIT_SLEEP);   // not the MMA issuers: they are the critical path
+#endif
+        }
         if (clock64() - t0 > ADEC_WATCHDOG_CYCLES) {
             printf("adec: mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x);
@@ -158,6 +162,7 @@ struct ConvArgs {
     // the next stream and are computed but never stored.  0 = one row space per stream (blockIdx-style b dimension).
     int stack_L, n_streams;
     int* err;            // device flag word: bit 1 = an activation left the fp16-split range (|a| >= 6e4)
+    unsigned long long* dbg;   // ADEC_KTRACE: {globaltimer at start, at end, SM cycles} of CTA 0, one record per launch (nullptr = off)
 };
 
 constexpr int CONV_STAGES = 4;

@@ -45,6 +45,8 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
 }
 
 template <int NT, int PREC> struct TcfCfg {
+    // One CTA per SM.  (Tried at NT = 32: two CTAs of 4 producer + 4 drain warps per SM - 0.38 -> 0.52 ms on the C = 32 unit, the
+    // 80-register budget spills and each pipeline has half the warps.)
     static constexpr int NPR = PREC == 3 ? 3 : 1;                  // weight planes per tap: hi | lo | hi * 2^-11
     static constexpr int NPL = PREC == 3 ? 2 : 1;                  // activation planes: hi | lo * 2^11
     static constexpr int TAP_BYTES = NPR * F16_KB * NT * 16;       // one (piece, tap) of weights
@@ -54,9 +56,16 @@ template <int NT, int PREC> struct TcfCfg {
     static constexpr int NPB = NT == 128 ? (NW == 3 ? 3 : 4) : (NW == 3 ? 6 : 8);   // TMEM partials
     static constexpr int MB = NT == 64 ? 2 : 1;                    // fused-intermediate buffers
     static constexpr int NDG = 2;                                  // drain groups (NT=32: each owns half a 32-column piece)
-    static constexpr int NPROD = NT == 128 ? 128 : 256;            // activation-producer threads
-    static constexpr int DRAIN0 = (128 + NPROD) / 32;
-    static constexpr int THREADS = 128 + NPROD + 128 * NDG;
+    // Producer threads: 8 warps wherever the 96-register budget of a 640-thread CTA holds the drain warps' accumulators - the producers
+    // are bound by the global loads they can keep in flight (ncu of the first f16 build, NT = 128 with 4 producer warps: long-scoreboard
+    // 10.5 stalls per issue, issue slots 22 % busy).  The fused NT = 128 unit (64 + 64 live accumulators) keeps 4 producer warps and
+    // 128 registers.  (setmaxnreg re-balancing was tried: ptxas caps the control / producer sections as asked but does not give the
+    // drain section more than the launch bound, so it only added spills.)
+#ifndef ADEC_NT128_PLAIN_NPROD
+#define ADEC_NT128_PLAIN_NPROD 256
+#endif
+    __host__ __device__ static constexpr int nprod(bool fuse) { return NT == 128 ? (fuse ? 128 : ADEC_NT128_PLAIN_NPROD) : 256; }
+    __host__ __device__ static constexpr int threads(bool fuse) { return 128 + nprod(fuse) + 128 * NDG; }
     static constexpr int MID_BYTES = NPL * F16_KB * F16_MIDP * 16; // one intermediate piece (32 channels)
     __host__ __device__ static constexpr int win_pitch(int wrows) { return ((wrows + 1) & ~3) + 2; }      // rows, == 2 mod 4: conflict-free producer stores
     __host__ __device__ static constexpr int win_bytes(int wrows) { return NPL * F16_KB * win_pitch(wrows) * 16; }
@@ -133,10 +142,10 @@ __device__ __forceinline__ float4 norm4(float4 x, const float* mean, const float
 }
 
 template <int NT, bool FUSE, int PRE, int PREC>
-__global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
+__global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f16_kernel(const ConvArgs a, int n_xtiles, int n_ytiles, int n_tiles) {
     using Cfg = TcfCfg<NT, PREC>;
     constexpr int S = Cfg::STAGES, CP = TC_CP, TT = TC_TT, NDG = Cfg::NDG, KB = F16_KB, MIDP = F16_MIDP;
-    constexpr int NPROD = Cfg::NPROD, DRAIN0 = Cfg::DRAIN0, NPB = Cfg::NPB, MB = Cfg::MB, NW = Cfg::NW;
+    constexpr int NPROD = Cfg::nprod(FUSE), DRAIN0 = (128 + NPROD) / 32, NPB = Cfg::NPB, MB = Cfg::MB, NW = Cfg::NW;
     constexpr int STAGE_BYTES = Cfg::STAGE_BYTES, TAP_BYTES = Cfg::TAP_BYTES, PLANE_B = KB * NT * 16;   // one weight plane of one tap
     constexpr int NCOL = NT / NDG;                       // accumulator registers per drain thread
     constexpr bool HALF = NCOL < CP;                     // NT=32: a drain group owns 16 of the piece's 32 columns
@@ -169,6 +178,9 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
 
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    unsigned long long kt0 = 0;
+    long long kc0 = 0;
+    if (a.dbg && blockIdx.x == 0 && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(kt0)); kc0 = clock64(); }
     const int gpp = (a.Ktaps + 1) >> 1;                            // groups per piece: tap pairs (+ one single tap)
     const int n_g1 = a.n_pieces * gpp;
     const int n_g2 = FUSE ? NT / CP : 0;
@@ -189,7 +201,6 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-
     if (warp == 0) {
         // ------------------------------------------------ weight producer: one bulk copy per group (1 or 2 taps)
         if (lane == 0) {
@@ -308,7 +319,10 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
     } else if (warp >= 4 && warp < DRAIN0) {
         // ------------------------------------------------ activation producers: one item = 8 channels (32 B of global) of one window row.
         // The loads of a piece are issued BEFORE the wait for a free window buffer, so global latency overlaps the MMAs that still read
-        // the buffer; a.n_wbuf (2..4) buffers let the producers run several pieces ahead.
+        // the buffer; a.n_wbuf (2..4) buffers let the producers run several pieces ahead.  (Tried and dropped: loading one piece AHEAD
+        // into a second register set - 200-500 B of spills per thread, 10.4 -> 17.3 ms per step - and a fully software-pipelined batch
+        // sequence with one general row resolver - twice the instructions, 11.3 -> 13.3 ms.  The producers are issue- and register-
+        // bound, not load-latency-bound.)
         const int pt = tid - 128;
         int wb = 0, wround = 0;                    // window piece counter wp = wround * n_wbuf + wb
         constexpr int RPP = NPROD / KB;            // window rows per pass
@@ -608,6 +622,11 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::THREADS, 1) tc_conv_f16_kern
     tc_fence_before();
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+    if (a.dbg && blockIdx.x == 0 && tid == 0) {
+        unsigned long long kt1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(kt1));
+        a.dbg[0] = kt0; a.dbg[1] = kt1; a.dbg[2] = (unsigned long long)(clock64() - kc0);
+    }
 }
 
 }  // namespace adec

@@ -390,19 +390,20 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # pre-warm: clocks / power state settle over the first ~second of load; these steps are not counted in W
+    # pre-warm: clocks / power state settle over the first ~second of load; these steps are not counted in W.  The clock sampler
+    # starts BEFORE the warm-up steps and nothing idles between warm-up and the timed region: a 250 ms pause there (round 1 slept to let
+    # the sampler spin up) lets some boxes drop their power state, and the first timed steps then run at ramping clocks (measured with
+    # tools/ktrace.py: same kernels, 10.2 ms per step back to back, but 12.4 ms in a timed region entered after the pause).
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     t_pre = time.time()
     while time.time() - t_pre < 1.5:
         step(0)
         torch.cuda.synchronize(dev)
     for i in range(args.warmup):
         step(i)
-    barrier()
     l0 = tx.launch_count + rx.launch_count + dec.launch_count
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.25)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()

@@ -148,6 +148,11 @@ int adec_range_error(adec_handle *h, void *stream);
 /* number of kernel launches issued by this handle since creation (bench.py's gpu_launches) */
 int64_t adec_launch_count(const adec_handle *h);
 
+/* Diagnostics (handles created with ADEC_KTRACE=1 in the environment): copies up to max_records {start ns, end ns, SM cycles} records
+ * of the tensor-core conv launches issued since the last call (CTA 0's globaltimer / clock64) and resets the trace; returns the
+ * number of records or -1.  Used to measure the effective SM clock and the gaps between back-to-back launches. */
+int adec_ktrace(adec_handle *h, unsigned long long *out, int max_records);
+
 /* Measured compute ceiling of the conv engine for bench.py's roofline: every SM streams `n_groups` x 12 tcgen05.mma (M = 128, N = NT,
  * kind 0 = tf32 / 1 = f16) from shared-memory operands in the engine's layout, nothing else; *tflops = dense TFLOP/s, *ms = duration
  * (may be NULL).  No handle needed. */

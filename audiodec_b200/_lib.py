@@ -70,6 +70,7 @@ SYMBOLS = {
     "adec_range_error": (c_int, [c_void_p, c_void_p]),
     "adec_launch_count": (c_int64, [c_void_p]),
     "adec_ktrace": (c_int, [c_void_p, ctypes.POINTER(ctypes.c_ulonglong), c_int]),
+    "adec_probe_mma_ex": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "adec_probe_mma": (c_int, [c_int, c_int, c_int, c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "adec_profile": (c_int, [c_void_p, c_int]),
     "adec_profile_report": (c_int, [c_void_p, c_char_p, c_int]),

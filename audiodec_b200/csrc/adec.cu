@@ -29,6 +29,9 @@
 using namespace adec;
 
 namespace {
+#ifdef ADEC_TIMELINE
+unsigned int* g_tl_last = nullptr;
+#endif
 
 thread_local std::string g_create_error;
 
@@ -244,6 +247,9 @@ struct adec_handle {
     int engine = 2;               // ADEC_CONV_PATH: 2 = f16 (tcgen05 kind::f16, default), 1 = tf32 (round-1 3xTF32), 0 = ffma (CUDA cores)
     bool use_tc = true;           // any tensor-core engine
     bool bf16 = false;            // cfg.compute_dtype == 1: bf16 operands (HiFi-GAN vocoder, f16 engine only)
+    int gspan = 0;                // ADEC_GSPAN: accumulation span of the f16 engine (ConvArgs::gspan)
+    int dbg_flags = 0;
+    int dbg_wdiv = 0;             // ADEC_DBG_WDIV (timing experiments, wrong results)
     bool stack_rows = true;       // ADEC_STACK_ROWS=0: never stack several streams' rows into one tile (A/B)
     unsigned long long* d_ktrace = nullptr;   // ADEC_KTRACE=1: per-launch {start ns, end ns, SM cycles} records (diagnostics)
     int ktrace_n = 0;
@@ -710,7 +716,21 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.y_bs = op.out_nct ? (long long)op.G * op.Cout * Tout : (long long)Tout * op.ldy;
             a.mid_act = op.mid_act;
             a.hist_rep = (rc.offline && op.up > 1) ? 1 : 0;
-            a.w_scale = op.w_scale; a.w2_scale = op.w2_scale; a.err = h->d_err;
+            a.w_scale = op.w_scale; a.w2_scale = op.w2_scale; a.err = h->d_err; a.dbg_wdiv = h->dbg_wdiv; a.dbg_flags = h->dbg_flags;
+            a.gspan = (h->gspan == 1 || (h->gspan == 2 && op.tcf && op.tcf->NT >= 128) || (h->gspan == 3 && op.tcf && op.tcf->NT >= 64)) ? 1 : 0;
+#ifdef ADEC_TIMELINE
+            // debug build: record CTA 1's event timeline of the op named by ADEC_TIMELINE_OP on its 4th launch, dump it to ADEC_TIMELINE_OUT
+            static unsigned int* tl_buf = nullptr;
+            static int tl_hits = 0;
+            if (const char* tlop = getenv("ADEC_TIMELINE_OP")) {
+                if (op.name == tlop && ++tl_hits == 4) {
+                    if (!tl_buf) cudaMalloc((void**)&tl_buf, (2 + 2 * 8192 * 6) * sizeof(unsigned int));
+                    cudaMemsetAsync(tl_buf, 0, (2 + 2 * 8192 * 6) * sizeof(unsigned int), rc.stream);
+                    a.tl = tl_buf;
+                    g_tl_last = tl_buf;
+                }
+            }
+#endif
             if (h->d_ktrace && h->ktrace_n < 4096) a.dbg = h->d_ktrace + 3 * (size_t)(h->ktrace_n++);
             if (op.tcf || op.tc) {
                 // persistent tensor-core kernels: one CTA per SM loops over (time tile, channel tile, stream) tiles
@@ -748,6 +768,28 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             }
         }
         if (e != cudaSuccess) return h->fail(fmt("launch of %s failed: %s", op.name.c_str(), cudaGetErrorString(e)));
+#ifdef ADEC_TIMELINE
+        if (op.kind == OP_CONV && getenv("ADEC_TIMELINE_OP") && op.name == getenv("ADEC_TIMELINE_OP")) {
+            static bool dumped = false;
+            if (g_tl_last && !dumped) {
+                dumped = true;
+                cudaStreamSynchronize(rc.stream);
+                std::vector<unsigned int> hb(2 + 2 * 8192 * 6);
+                cudaMemcpy(hb.data(), g_tl_last, hb.size() * sizeof(unsigned int), cudaMemcpyDeviceToHost);
+                const char* outp = getenv("ADEC_TIMELINE_OUT");
+                if (FILE* f = fopen(outp ? outp : "timeline.txt", "w")) {
+                    fprintf(f, "# %s\n", op.name.c_str());
+                    for (unsigned r = 0; r < 6; ++r)
+                        for (unsigned i = 0; i < 8192; ++i) {
+                            const unsigned w0 = hb[2 + 2 * (8192 * r + i)], w1 = hb[3 + 2 * (8192 * r + i)];
+                            if (!w0 && !w1) break;
+                            fprintf(f, "%u %u %u\n", w0 >> 24, w0 & 0xffffffu, w1);
+                        }
+                    fclose(f);
+                }
+            }
+        }
+#endif
         ++h->launches;
         if (h->profiling) {
             cudaEventRecord(ev1, rc.stream);
@@ -1141,6 +1183,9 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     }
     h->use_tc = h->engine != 0;
     if (const char* sr = getenv("ADEC_STACK_ROWS")) h->stack_rows = atoi(sr) != 0;
+    if (const char* gs = getenv("ADEC_GSPAN")) h->gspan = atoi(gs);
+    if (const char* wd = getenv("ADEC_DBG_WDIV")) h->dbg_wdiv = atoi(wd);
+    if (const char* df = getenv("ADEC_DBG_FLAGS")) h->dbg_flags = atoi(df);
     if (const char* kt = getenv("ADEC_KTRACE")) {
         if (atoi(kt)) { DeviceGuard dgk(device); cudaMalloc((void**)&h->d_ktrace, 4096 * 3 * sizeof(unsigned long long)); }
     }
@@ -1427,6 +1472,7 @@ int adec_codec_host(adec_handle* enc, adec_handle* dec, const float* x_host, int
         int herr = 0;
         CK(enc, cudaMemcpy(&herr, hh->d_err, sizeof(int), cudaMemcpyDeviceToHost));
         if (herr) CK(enc, cudaMemset(hh->d_err, 0, sizeof(int)));
+        if (hh->dbg_flags || hh->dbg_wdiv) continue;      // timing experiments: results are wrong on purpose
         if (herr & 1) return enc->fail("lookup: index out of range");
         if (herr & 2) return enc->fail("an activation left the range of the fp16-split tensor-core engine (|a| >= 6e4); use ADEC_CONV_PATH=tf32");
         if (hh == dec) break;     // enc == dec
@@ -1490,17 +1536,17 @@ int adec_ktrace(adec_handle* h, unsigned long long* out, int max_records) {
     return n;
 }
 
-int adec_probe_mma(int device, int kind, int NT, int n_groups, double* tflops, double* ms) {
-    if (!tflops || (kind != 0 && kind != 1) || NT < 16 || NT > 256 || NT % 16 || n_groups < 1) { g_create_error = "probe_mma: bad argument"; return 1; }
+int adec_probe_mma_ex(int device, int kind, int NT, int n_groups, int a_off_rows, int a_pitch_rows, int tap_step_rows, int n_issuers, double* tflops, double* ms) {
+    if (!tflops || (kind != 0 && kind != 1) || NT < 16 || NT > 256 || NT % 16 || n_groups < 1 || a_off_rows < 0 || a_pitch_rows < 128 || a_pitch_rows > 256 || tap_step_rows < 0 || tap_step_rows > 16 || n_issuers < 1 || n_issuers > 4) { g_create_error = "probe_mma: bad argument"; return 1; }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { g_create_error = "probe_mma: no usable CUDA device"; return 1; }
     DeviceGuard dg(device);
     int n_sms = 0;
     cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, device);
-    const int smem = 8 * 2 * (128 + NT) * 16;
+    const int smem = ((8 * 2 * a_pitch_rows + a_off_rows + 8 * tap_step_rows + 8) * 16 & ~127) + 8 * 2 * NT * 16;
     auto launch = [&](cudaStream_t s) {
-        if (kind == 0) { cudaFuncSetAttribute(mma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); mma_probe_kernel<0><<<n_sms, 128, smem, s>>>(NT, n_groups); }
-        else { cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); mma_probe_kernel<1><<<n_sms, 128, smem, s>>>(NT, n_groups); }
+        if (kind == 0) { cudaFuncSetAttribute(mma_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); mma_probe_kernel<0><<<n_sms, 128, smem, s>>>(NT, n_groups, a_off_rows, a_pitch_rows, tap_step_rows, n_issuers); }
+        else { cudaFuncSetAttribute(mma_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); mma_probe_kernel<1><<<n_sms, 128, smem, s>>>(NT, n_groups, a_off_rows, a_pitch_rows, tap_step_rows, n_issuers); }
     };
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
@@ -1517,6 +1563,10 @@ int adec_probe_mma(int device, int kind, int NT, int n_groups, double* tflops, d
     *tflops = flops / (t * 1e-3) / 1e12;
     if (ms) *ms = t;
     return 0;
+}
+
+int adec_probe_mma(int device, int kind, int NT, int n_groups, double* tflops, double* ms) {
+    return adec_probe_mma_ex(device, kind, NT, n_groups, 0, 128, 0, 1, tflops, ms);
 }
 
 int adec_profile(adec_handle* h, int enable) {

@@ -32,6 +32,22 @@
 
 namespace adec {
 
+// -DADEC_TIMELINE: CTA 1 records {event << 24 | index, clock} pairs into ConvArgs::tl (tools/timeline_f16.py prints them)
+#ifdef ADEC_TIMELINE
+// every recording thread owns a region of 8192 records and a private counter: plain stores, no atomics (an atomic's round trip would
+// stall the recording warp for ~600 cycles per event)
+#define ADEC_TL_DECL(role) unsigned int tl_n = 0; unsigned int* const tl_base = a.tl ? a.tl + 2 + 2 * 8192 * (role) : nullptr
+#define ADEC_TL(code, idx)                                                                        \
+    do {                                                                                          \
+        if (tl_base && blockIdx.x == 1 && tl_n < 8192u) {                                         \
+            tl_base[2 * tl_n] = ((unsigned)(code) << 24) | ((unsigned)(idx) & 0xffffffu); tl_base[2 * tl_n + 1] = (unsigned)clock64(); ++tl_n; \
+        }                                                                                         \
+    } while (0)
+#else
+#define ADEC_TL_DECL(role) do { } while (0)
+#define ADEC_TL(code, idx) do { } while (0)
+#endif
+
 constexpr int F16_KB = TC_CP / 8;      // 16-byte K blocks (8 channels) per 32-channel piece and plane
 constexpr int F16_MIDP = 128;          // rows of the fused intermediate operand (one row per drain lane: 16-byte stores are conflict-free)
 constexpr float F16_LO_SCALE = 2048.f; // 2^11
@@ -79,6 +95,20 @@ template <int NT, int PREC> struct TcfCfg {
         return 512 + (size_t)STAGES * STAGE_BYTES + (size_t)n_wbuf(wrows, fuse) * win_bytes(wrows) + (fuse ? (size_t)MB * MID_BYTES : 0);
     }
 };
+
+// 256-bit global accesses (sm_100: LDG.E.256 / STG.E.256): one instruction and one full 32-byte sector per lane where two 128-bit
+// accesses would each touch half a sector - the epilogue's row-per-lane stores and skip loads cost one LSU line transaction per lane
+// and instruction, so halving the instructions halves that cost.  Addresses must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const float* p, float4& u, float4& v) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(u.x), "=f"(u.y), "=f"(u.z), "=f"(u.w), "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+}
+__device__ __forceinline__ void stg256(float* p, const float* v) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+                 "f"(v[6]), "f"(v[7])
+                 : "memory");
+}
 
 // 8 consecutive channels of one row -> one 16-byte hi block (+ one lo block)
 template <int PREC>
@@ -182,8 +212,14 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
     long long kc0 = 0;
     if (a.dbg && blockIdx.x == 0 && tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(kt0)); kc0 = clock64(); }
     const int gpp = (a.Ktaps + 1) >> 1;                            // groups per piece: tap pairs (+ one single tap)
-    const int n_g1 = a.n_pieces * gpp;
-    const int n_g2 = FUSE ? NT / CP : 0;
+    // TMEM partials per tile.  gspan = 0: one partial per group (4 main accumulation steps, then round-to-nearest register adds);
+    // gspan = 1: one partial per 32-channel PIECE (all its taps: 14 main steps at K = 7) and one for the whole 1x1 conv - 3.5x fewer
+    // TMEM -> register round trips, which bound the wide layers (timeline: ~2400 cycles of tcgen05.ld latency per partial at NT = 128
+    // against 816 cycles of MMAs per group); a single warp issues in that mode so every accumulator sees its MMAs in program order.
+    const bool span = a.gspan != 0;
+    const int n_g1 = span ? a.n_pieces : a.n_pieces * gpp;
+    const int n_g2 = FUSE ? (span ? 1 : NT / CP) : 0;
+    const int n_s2 = FUSE ? NT / CP : 0;                          // weight stages of the 1x1 conv
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
@@ -205,14 +241,18 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         // ------------------------------------------------ weight producer: one bulk copy per group (1 or 2 taps)
         if (lane == 0) {
             int c = 0;
+            ADEC_TL_DECL(0);
             auto stream = [&](const unsigned char* base, int pieces, int taps) {
                 for (int p = 0; p < pieces; ++p)
                     for (int t0 = 0; t0 < taps; t0 += 2, ++c) {
                         const int s = c % S, it = c / S;
                         const uint32_t bytes = (uint32_t)(taps - t0 >= 2 ? 2 : 1) * TAP_BYTES;
                         if (it > 0) mbar_wait(&b_empty[s], (it - 1) & 1, 100);
-                        mbar_arrive_expect_tx(&b_full[s], bytes);
-                        bulk_g2s(bst + s * STAGE_BYTES, base + ((long long)p * taps + t0) * TAP_BYTES, bytes, &b_full[s]);
+                        ADEC_TL(1, c);
+                        if (a.dbg_wdiv < 0) { mbar_arrive(&b_full[s]); continue; }
+                        const uint32_t lb = a.dbg_wdiv > 1 ? (bytes / (uint32_t)a.dbg_wdiv) & ~15u : bytes;
+                        mbar_arrive_expect_tx(&b_full[s], lb);
+                        bulk_g2s(bst + s * STAGE_BYTES, base + ((long long)p * taps + t0) * TAP_BYTES, lb, &b_full[s]);
                     }
             };
             const unsigned char* w1 = reinterpret_cast<const unsigned char*>(a.w);
@@ -225,12 +265,12 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 while (it.tile < n_tiles) {
                     it.next(gridDim.x);
                     if (it.tile < n_tiles) stream(w1_of(it.y), a.n_pieces, a.Ktaps);
-                    stream(w2, n_g2, 1);
+                    stream(w2, n_s2, 1);
                 }
             } else {
                 for (; it.tile < n_tiles; it.next(gridDim.x)) {
                     stream(w1_of(it.y), a.n_pieces, a.Ktaps);
-                    if (FUSE) stream(w2, n_g2, 1);
+                    if (FUSE) stream(w2, n_s2, 1);
                 }
             }
         }
@@ -238,19 +278,26 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         // ------------------------------------------------ MMA issuers (groups round robin)
         const int mw = warp - 1;
         int c = 0, mp = 0;
+        ADEC_TL_DECL(1 + mw);
         int wb = 0, wround = 0;                                   // window piece counter wp = wround * n_wbuf + wb
         const uint32_t b_lbo = (uint32_t)NT * 16u;
         const uint32_t wbuf0_u = smem_u32(wbuf0), mbuf_u = smem_u32(mbuf), bst_u = smem_u32(bst);
         // one group: ntaps (1 or 2) taps of one 32-channel piece; tap t reads window rows shifted by row_off + t * tap_step bytes
-        auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off, uint32_t tap_step, int ntaps) {
-            const int s = c % S, pb = c % NPB;
+        int qc = 0;                                                // partial counter (== c when every group has its own partial)
+        // one group: ntaps (1 or 2) taps of one 32-channel piece; tap t reads window rows shifted by row_off + t * tap_step bytes.
+        // first / last: the group opens / closes its TMEM partial (always both unless a.gspan).
+        auto issue_group = [&](uint32_t a_hi, uint32_t a_lo, uint32_t lbo, uint32_t row_off, uint32_t tap_step, int ntaps, bool first, bool last) {
+            const int s = c % S, pb = qc % NPB;
+            if (lane == 0) ADEC_TL(2, c);
             mbar_wait(&b_full[s], (c / S) & 1, 300);
-            if (c >= NPB) mbar_wait(&p_empty[pb], ((c / NPB) - 1) & 1, 400);
+            if (lane == 0) ADEC_TL(3, c);
+            if (first && qc >= NPB) mbar_wait(&p_empty[pb], ((qc / NPB) - 1) & 1, 400);
             tc_fence_after();
+            if (lane == 0) ADEC_TL(4, c);
             const uint32_t bw = bst_u + (uint32_t)s * STAGE_BYTES;
             const uint32_t acc = tmem + (uint32_t)pb * NT;
             if (elect_one()) {
-                uint32_t accum = 0u;
+                uint32_t accum = first ? 0u : 1u;
                 if (PREC == 3) {
                     // small terms first: A_lo x W_his, A_hi x W_lo
                     for (int t = 0; t < ntaps; ++t)
@@ -274,21 +321,27 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                         accum = 1u;
                     }
                 umma_commit(&b_empty[s]);
-                umma_commit(&p_full[pb]);
+                if (last) umma_commit(&p_full[pb]);
             }
             __syncwarp();
+            if (lane == 0) ADEC_TL(5, c);
         };
         const uint32_t lbo1 = (uint32_t)wrp * 16u, lbo2 = (uint32_t)MIDP * 16u;
         const uint32_t tap_step = (uint32_t)a.dil * 16u;
         auto gemm1 = [&]() {        // one tile's conv over its window pieces
             for (int p = 0; p < a.n_pieces; ++p) {
                 const int buf = wb;
+                if (lane == 0 && mw == 0) ADEC_TL(6, p);
                 mbar_wait(&w_full[buf], wround & 1, 200);
+                if (lane == 0 && mw == 0) ADEC_TL(7, p);
                 if (++wb == a.n_wbuf) { wb = 0; ++wround; }
                 const uint32_t a_hi = wbuf0_u + (uint32_t)buf * (uint32_t)win_b;
                 const uint32_t a_lo = a_hi + (uint32_t)KB * lbo1;
-                for (int t0 = 0; t0 < a.Ktaps; t0 += 2, ++c)
-                    if (c % NW == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)t0 * tap_step, tap_step, a.Ktaps - t0 >= 2 ? 2 : 1);
+                for (int t0 = 0; t0 < a.Ktaps; t0 += 2, ++c) {
+                    const bool first = !span || t0 == 0, last = !span || t0 + 2 >= a.Ktaps;
+                    if (span ? mw == 0 : c % NW == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)t0 * tap_step, tap_step, a.Ktaps - t0 >= 2 ? 2 : 1, first, last);
+                    if (last) ++qc;
+                }
                 if (elect_one()) umma_commit(&w_empty[buf]);
                 __syncwarp();
             }
@@ -298,7 +351,11 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 const int mb = mp % MB;
                 mbar_wait(&m_full[mb], (mp / MB) & 1, 250);
                 const uint32_t m_hi = mbuf_u + (uint32_t)mb * Cfg::MID_BYTES;
-                if (c % NW == mw) issue_group(m_hi, m_hi + (uint32_t)KB * lbo2, lbo2, 0u, 0u, 1);
+                {
+                    const bool first = !span || p == 0, last = !span || p == NT / CP - 1;
+                    if (span ? mw == 0 : c % NW == mw) issue_group(m_hi, m_hi + (uint32_t)KB * lbo2, lbo2, 0u, 0u, 1, first, last);
+                    if (last) ++qc;
+                }
                 // buffer mb is free for piece mp + MB, which drain group (mp + MB) % NDG writes: signal THAT group's barrier
                 if (elect_one()) umma_commit(&m_empty[HALF ? 0 : (mp + MB) % NDG]);
                 __syncwarp();
@@ -324,6 +381,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         // sequence with one general row resolver - twice the instructions, 11.3 -> 13.3 ms.  The producers are issue- and register-
         // bound, not load-latency-bound.)
         const int pt = tid - 128;
+        ADEC_TL_DECL(4);
         int wb = 0, wround = 0;                    // window piece counter wp = wround * n_wbuf + wb
         constexpr int RPP = NPROD / KB;            // window rows per pass
         constexpr int UNR = NPROD == 128 ? 5 : 3;  // rows in flight per thread (2 x 128-bit loads each): one pass covers 160 / 192 rows
@@ -338,6 +396,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
             const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
             for (int p = 0; p < a.n_pieces; ++p) {
                 const int buf = wb;
+                if (pt == 0) ADEC_TL(8, p);
                 const uint32_t wpar = (uint32_t)(wround - 1) & 1u;
                 bool waited = wround == 0;
                 if (++wb == a.n_wbuf) { wb = 0; ++wround; }
@@ -348,7 +407,9 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 if (a.RG > 1) { r = q >> a.lgCin; ci = q & (a.Cin - 1); }
                 const long long i_first = (long long)j0 * a.RG + r;
                 const long long i_last = (long long)(j0 + wrows - 1) * a.RG + r;
-                if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM && !halves && !a.stack_L) {
+                if ((a.dbg_flags & 1) && i_first >= a.P && i_last - a.P < a.T) {
+                    if (!waited) { mbar_wait(&w_empty[buf], wpar, 500); waited = true; }
+                } else if (i_first >= a.P && i_last - a.P < a.T && PRE != ACT_NORM && !halves && !a.stack_L) {
                     // interior piece: every row comes from the chunk
                     const float* xp = xg + ci + (i_first - a.P + (long long)m0 * a.RG) * a.ldx;
                     const long long xstep = (long long)RPP * a.RG * a.ldx;
@@ -356,10 +417,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                         float4 u[UNR], v[UNR];
 #pragma unroll
                         for (int k = 0; k < UNR; ++k)
-                            if (mb + k * RPP < wrows) {
-                                u[k] = __ldg(reinterpret_cast<const float4*>(xp + k * xstep));
-                                v[k] = __ldg(reinterpret_cast<const float4*>(xp + k * xstep) + 1);
-                            }
+                            if (mb + k * RPP < wrows) ldg256(xp + k * xstep, u[k], v[k]);
                         if (!waited) { mbar_wait(&w_empty[buf], wpar, 500); waited = true; }
 #pragma unroll
                         for (int k = 0; k < UNR; ++k) {
@@ -421,6 +479,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 }
                 fence_async_smem();
                 mbar_arrive(&w_full[buf]);
+                if (pt == 0) ADEC_TL(9, p);
             }
             // ---- new causal state (conv_layer.py:155): written by the CTA whose tile holds the stream's last output row
             if (co_tile == 0 && g < a.st_groups && a.P > 0) {
@@ -463,6 +522,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         const int row = (warp & 3) * 32 + lane;
         const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
         float racc[NCOL];
+        ADEC_TL_DECL(5);
         constexpr bool PREFETCH_RES = FUSE && NT <= 64;     // registers permitting
         float4 rpre[PREFETCH_RES ? PPG : 1][UC / 4];
         int c = 0, mq = 0;
@@ -471,8 +531,10 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         auto drain = [&](float (&acc)[NCOL], int ngroups) {
             for (int gi = 0; gi < ngroups; ++gi, ++c) {
                 const int pb = c % NPB;
+                if (row == 0 && dg == 0) ADEC_TL(10, c);
                 mbar_wait(&p_full[pb], (c / NPB) & 1, 600);
                 tc_fence_after();
+                if (row == 0 && dg == 0) ADEC_TL(11, c);
                 if (HALF) {
                     uint32_t r0[16];
                     tmem_ld16(tmem + lane_base + (uint32_t)pb * NT + (uint32_t)dg * UC, r0);
@@ -496,6 +558,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 }
                 tc_fence_before();
                 mbar_arrive(&p_empty[pb]);
+                if (row == 0 && dg == 0) ADEC_TL(12, c);
             }
         };
         float oacc[PIPE ? NCOL : 1];                         // PIPE: 1x1-conv sums of tile i while racc already holds tile i+1
@@ -558,7 +621,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                         const int co_l = co_tile * NT + (HALF ? dg * UC : (pl * NDG + dg) * CP);
                         const float* rp = a.res + (long long)bo * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
 #pragma unroll
-                        for (int i = 0; i < UC / 4; ++i) rpre[pl][i] = __ldg(reinterpret_cast<const float4*>(rp) + i);
+                        for (int i = 0; i < UC / 4; i += 2) ldg256(rp + 4 * i, rpre[pl][i], rpre[pl][i + 1]);
                     }
                 }
                 if (PIPE) {
@@ -571,6 +634,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                     drain(racc, n_g2);
                 }
             }
+            if (row == 0 && dg == 0) ADEC_TL(13, tile);
             float* const outv = PIPE ? oacc : racc;
             const float oscale = FUSE ? a.w2_scale : a.w_scale;
             // ---- epilogue: row `row` of the tile, this group's PPG pieces of 32 channels
@@ -593,8 +657,10 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                         const float* rp = a.res + (long long)bo * a.res_bs + (long long)t * a.ldr + g * a.r_goff + co_l;
                         float4 r4[UC / 4];
 #pragma unroll
-                        for (int i = 0; i < UC / 4; ++i)
-                            r4[i] = PREFETCH_RES ? rpre[PREFETCH_RES ? pl : 0][i] : __ldg(reinterpret_cast<const float4*>(rp) + i);   // all loads in flight first
+                        for (int i = 0; i < UC / 4; i += 2) {                                                                      // all loads in flight first
+                            if (PREFETCH_RES) { r4[i] = rpre[PREFETCH_RES ? pl : 0][i]; r4[i + 1] = rpre[PREFETCH_RES ? pl : 0][i + 1]; }
+                            else ldg256(rp + 4 * i, r4[i], r4[i + 1]);
+                        }
 #pragma unroll
                         for (int i = 0; i < UC / 4; ++i) {
                             v[4 * i] = r4[i].x + v[4 * i]; v[4 * i + 1] = r4[i].y + v[4 * i + 1];
@@ -610,8 +676,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                     } else {
                         float* yp = a.y + (long long)bo * a.y_bs + (long long)t * a.ldy + g * a.y_goff + co_l;
 #pragma unroll
-                        for (int i = 0; i < UC / 4; ++i)
-                            *(reinterpret_cast<float4*>(yp) + i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                        for (int i = 0; i < UC / 8; ++i) stg256(yp + 8 * i, v + 8 * i);
                     }
                 }
             }

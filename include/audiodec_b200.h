@@ -157,6 +157,11 @@ int adec_ktrace(adec_handle *h, unsigned long long *out, int max_records);
  * kind 0 = tf32 / 1 = f16) from shared-memory operands in the engine's layout, nothing else; *tflops = dense TFLOP/s, *ms = duration
  * (may be NULL).  No handle needed. */
 int adec_probe_mma(int device, int kind, int NT, int n_groups, double *tflops, double *ms);
+/* Same with the A operand placed like a conv window: first row a_off_rows, a_pitch_rows rows per 16-byte K block (LBO), and MMA k of a
+ * group reading rows shifted by (k % 7) * tap_step_rows - measures what a tap's row-shifted, non-128-byte-aligned start address costs; n_issuers (1..4) warps issue the
+ * groups round robin, each group on its own TMEM accumulator, without ordering between the warps. */
+int adec_probe_mma_ex(int device, int kind, int NT, int n_groups, int a_off_rows, int a_pitch_rows, int tap_step_rows, int n_issuers,
+                      double *tflops, double *ms);
 
 /* Per-launch CUDA-event timing on the handle's stream (bench.py's roofline leg).  adec_profile(h,1) starts
  * recording around every kernel launch, adec_profile(h,0) stops and clears.  adec_profile_report writes one line

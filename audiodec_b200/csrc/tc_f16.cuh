@@ -60,6 +60,19 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t da, uint64_t 
         : "memory");
 }
 
+// Same MMA with the two shared-memory descriptors given by their LOW words (start address >> 4 | LBO >> 4 << 16); the high word
+// (SBO = 128 B, descriptor version 1) is the constant 0x4008.  The issuing lane advances the low words by small additions, which keeps
+// its instruction count per MMA at ~4 uniform-datapath instructions (umma_desc() from scratch: ~11 - at N <= 64 the issue rate of
+// one lane, ~80 cycles per MMA, was below what the tensor pipe accepts, 43 / 51 cycles: tools/probe_align.py).
+__device__ __forceinline__ void umma_f16_lo(uint32_t tmem_d, uint32_t a_lo_word, uint32_t b_lo_word, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n .reg .pred p;\n .reg .b64 da, db;\n setp.ne.b32 p, %4, 0;\n mov.b64 da, {%1, %5};\n mov.b64 db, {%2, %5};\n"
+        " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}" ::"r"(tmem_d),
+        "r"(a_lo_word), "r"(b_lo_word), "r"(idesc), "r"(accumulate), "r"(0x4008u)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t umma_lo_word(uint32_t saddr, uint32_t lbo_bytes) { return ((saddr & 0x3FFFF) >> 4) | (((lbo_bytes >> 4) & 0x3FFF) << 16); }
+
 template <int NT, int PREC> struct TcfCfg {
     // One CTA per SM.  (Tried at NT = 32: two CTAs of 4 producer + 4 drain warps per SM - 0.38 -> 0.52 ms on the C = 32 unit, the
     // 80-register budget spills and each pipeline has half the warps.)
@@ -298,26 +311,31 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
             const uint32_t acc = tmem + (uint32_t)pb * NT;
             if (elect_one()) {
                 uint32_t accum = first ? 0u : 1u;
+                // descriptor low words; all byte offsets are multiples of 16, so they advance by (bytes >> 4) without touching the LBO field
+                const uint32_t ah0 = umma_lo_word(a_hi + row_off, lbo), al0 = umma_lo_word(a_lo + row_off, lbo);
+                const uint32_t b0 = umma_lo_word(bw, b_lbo);
+                const uint32_t a_ks = (2u * lbo) >> 4, a_t = tap_step >> 4;
+                constexpr uint32_t B_KS = (2u * NT * 16u) >> 4, B_T = (uint32_t)TAP_BYTES >> 4, B_PL = (uint32_t)PLANE_B >> 4;
                 if (PREC == 3) {
                     // small terms first: A_lo x W_his, A_hi x W_lo
-                    for (int t = 0; t < ntaps; ++t)
 #pragma unroll
-                        for (int ks = 0; ks < KB / 2; ++ks) {
-                            umma_f16(acc, umma_desc(a_lo + (uint32_t)(ks * 2) * lbo + row_off + t * tap_step, lbo),
-                                     umma_desc(bw + t * TAP_BYTES + 2 * PLANE_B + (uint32_t)(ks * 2) * b_lbo, b_lbo), IDESC, accum);
+                    for (int t = 0; t < 2; ++t)
+#pragma unroll
+                        for (int ks = 0; ks < KB / 2; ++ks) if (t < ntaps) {
+                            umma_f16_lo(acc, al0 + (uint32_t)t * a_t + (uint32_t)ks * a_ks, b0 + (uint32_t)t * B_T + 2u * B_PL + (uint32_t)ks * B_KS, IDESC, accum);
                             accum = 1u;
                         }
-                    for (int t = 0; t < ntaps; ++t)
+#pragma unroll
+                    for (int t = 0; t < 2; ++t)
 #pragma unroll
                         for (int ks = 0; ks < KB / 2; ++ks)
-                            umma_f16(acc, umma_desc(a_hi + (uint32_t)(ks * 2) * lbo + row_off + t * tap_step, lbo),
-                                     umma_desc(bw + t * TAP_BYTES + PLANE_B + (uint32_t)(ks * 2) * b_lbo, b_lbo), IDESC, 1u);
+                            if (t < ntaps) umma_f16_lo(acc, ah0 + (uint32_t)t * a_t + (uint32_t)ks * a_ks, b0 + (uint32_t)t * B_T + B_PL + (uint32_t)ks * B_KS, IDESC, 1u);
                 }
-                for (int t = 0; t < ntaps; ++t)
 #pragma unroll
-                    for (int ks = 0; ks < KB / 2; ++ks) {
-                        umma_f16(acc, umma_desc(a_hi + (uint32_t)(ks * 2) * lbo + row_off + t * tap_step, lbo),
-                                 umma_desc(bw + t * TAP_BYTES + (uint32_t)(ks * 2) * b_lbo, b_lbo), IDESC, accum);
+                for (int t = 0; t < 2; ++t)
+#pragma unroll
+                    for (int ks = 0; ks < KB / 2; ++ks) if (t < ntaps) {
+                        umma_f16_lo(acc, ah0 + (uint32_t)t * a_t + (uint32_t)ks * a_ks, b0 + (uint32_t)t * B_T + (uint32_t)ks * B_KS, IDESC, accum);
                         accum = 1u;
                     }
                 umma_commit(&b_empty[s]);

@@ -1378,7 +1378,7 @@ cudaError_t launch_rvq(const adec_handle* h, RvqArgs a, cudaStream_t s, int* cos
     static int per_sm[64] = {0};
     auto kern = rvq_kernel<64, 4, FP>;
     const int dev = h->device;
-    const auto smem_of = [&](int n_pass) { const int FR = n_pass * FP; return (size_t)FR * (2 * 64 + 1 + 2 * (RVQ_THREADS / 32) + a.nq) * 4; };
+    const auto smem_of = [&](int n_pass) { const int FR = n_pass * FP; return (size_t)FR * (3 * 64 + 1 + 2 * (RVQ_THREADS / 32) + a.nq) * 4; };
     if (dev < 64 && !per_sm[dev]) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
         int nb = 0;
@@ -1387,7 +1387,7 @@ cudaError_t launch_rvq(const adec_handle* h, RvqArgs a, cudaStream_t s, int* cos
     }
     const long long nfr = (long long)a.B * a.F, slots = (long long)h->n_sms * per_sm[dev < 64 ? dev : 0];
     int n_pass = (int)((nfr + slots * FP - 1) / (slots * FP));
-    n_pass = std::max(1, std::min(n_pass, 96 / FP));                 // <= 96 frames of residuals + zq in shared memory
+    n_pass = std::max(1, std::min(n_pass, 96 / FP));                 // <= 96 frames of residuals (x1, x2) + zq in shared memory (79 KB)
     if (cost) { *cost = n_pass * (FP + 2) * (int)((nfr + slots * n_pass * FP - 1) / (slots * n_pass * FP)); return cudaSuccess; }
     a.n_pass = n_pass;
     const long long FR = (long long)n_pass * FP;

@@ -561,7 +561,9 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
     const int FR = a.n_pass * FP;
     float* r = rvq_smem;                               // [FR][D] residuals
     float* zq = r + FR * D;                            // [FR][D] sum of the chosen codewords
-    float* x2 = zq + FR * D;                           // [FR]
+    float* r2 = zq + FR * D;                           // [FR][D] 2 * residual (exact): the multiplicand of the distance GEMM, kept so that the
+                                                       //         inner loop is FFMA + one broadcast LDS.128 per 16 of them (was + 4 FMUL)
+    float* x2 = r2 + FR * D;                           // [FR]
     float* wv = x2 + FR;                               // [FR][NW]
     int* wi = reinterpret_cast<int*>(wv + FR * NW);    // [FR][NW]
     int* best = wi + FR * NW;                          // [nq][FR] local indices of every stage (for the packed frame)
@@ -577,6 +579,7 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
             v = a.z[(bb * D + k) * a.F + ff];        // quantizer.py:43 z.transpose(2,1)
         }
         r[f * D + k] = v;
+        r2[f * D + k] = 2.0f * v;
         zq[f * D + k] = 0.f;
     }
     __syncthreads();
@@ -630,8 +633,8 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
                     for (int m = 0; m < NPT; ++m) en[kk][m] = __ldg(E + (long long)(kn + kk) * N + tid + m * RVQ_THREADS);
 #pragma unroll
                 for (int f = 0; f < FP; ++f) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(&r[(fh + f) * D + k]);
-                    const float rk[4] = {2.0f * r4.x, 2.0f * r4.y, 2.0f * r4.z, 2.0f * r4.w};
+                    const float4 r4 = *reinterpret_cast<const float4*>(&r2[(fh + f) * D + k]);
+                    const float rk[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk)
 #pragma unroll
@@ -682,7 +685,9 @@ __global__ void __launch_bounds__(RVQ_THREADS) rvq_kernel(const RvqArgs a) {
             const float rv = r[i];
             const float q = __ldg(E + (long long)k * N + best[st * FR + f]);
             const float qq = __fadd_rn(rv, __fsub_rn(q, rv));
-            r[i] = __fsub_rn(rv, qq);
+            const float rn = __fsub_rn(rv, qq);
+            r[i] = rn;
+            r2[i] = 2.0f * rn;
             zq[i] = st == 0 ? q : __fadd_rn(zq[i], q);
         }
         __syncthreads();

@@ -74,6 +74,7 @@ class MultiStreamCodecServer:
         self._stop = threading.Event()
         self._thread: Optional[threading.Thread] = None
         self._x_host = None                    # pinned staging buffers, allocated on the first step
+        self._x_np = None
         self._y_host = None
 
     # ------------------------------------------------------------------ producer / consumer side (audio callbacks)
@@ -105,6 +106,7 @@ class MultiStreamCodecServer:
         if self._x_host is None:
             pin = like.type == "cuda"
             self._x_host = torch.zeros(self.n_streams, 1, self.frame_size, dtype=torch.float32, pin_memory=pin)
+            self._x_np = self._x_host.numpy()          # same memory: frames are copied in with numpy (≈1 us each, no tensor wrappers)
         return self._x_host
 
     def step(self) -> int:
@@ -112,15 +114,17 @@ class MultiStreamCodecServer:
         t0 = self._clock()
         dev = self.device if self.device is not None else torch.device("cpu")
         x_host = self._staging(dev)
+        x_np = self._x_np
         stamps: List[Optional[float]] = [None] * self.n_streams
         with self._lock:
             for s in range(self.n_streams):
-                if self._in[s]:
-                    f, t = self._in[s].popleft()
-                    x_host[s, 0].copy_(torch.from_numpy(f))
+                q = self._in[s]
+                if q:
+                    f, t = q.popleft()
+                    x_np[s, 0] = f
                     stamps[s] = t
                 else:
-                    x_host[s].zero_()
+                    x_np[s, 0] = 0.0
                     self.stats[s].underruns += 1
         live = sum(t is not None for t in stamps)
         with torch.no_grad():
@@ -137,17 +141,27 @@ class MultiStreamCodecServer:
                 zq = self.rx_encoder.lookup(self.rx_encoder.unpack(packed))
             else:
                 zq = self.rx_encoder.lookup(self.tx_encoder.quantize(z))
-            y = self.decoder.decode(zq)                                         # utils/audiodec.py:104-106
-            y_host = y.detach().to("cpu")                                       # synchronises with the launches above
+            y = self.decoder.decode(zq).detach()                                # utils/audiodec.py:104-106
+            if y.device.type == "cuda":
+                # device -> PINNED host buffer (a pageable destination is staged through a driver bounce buffer), then one synchronise
+                if self._y_host is None or self._y_host.shape != y.shape:
+                    self._y_host = torch.empty(y.shape, dtype=y.dtype, pin_memory=True)
+                self._y_host.copy_(y, non_blocking=True)
+                torch.cuda.current_stream(y.device).synchronize()
+                y_host = self._y_host
+            else:
+                y_host = y
         now = self._clock()
-        y_np = y_host.numpy().reshape(self.n_streams, -1)
+        y_all = y_host.numpy().reshape(self.n_streams, -1)[:, :self.frame_size].copy()    # one copy; the queues hold row views of it
         with self._lock:
             for s in range(self.n_streams):
-                if stamps[s] is None:
+                t = stamps[s]
+                if t is None:
                     continue                        # silence went in to keep the stream's state in step; nothing to play
-                self._out[s].append(y_np[s, :self.frame_size].copy())
-                self.stats[s].n_frames += 1
-                self.stats[s].latencies.append(now - stamps[s])
+                st = self.stats[s]
+                self._out[s].append(y_all[s])
+                st.n_frames += 1
+                st.latencies.append(now - t)
         self.step_times.append(now - t0)
         return live
 

@@ -4,7 +4,7 @@ import csv, re, sys
 path = sys.argv[1]; n = int(sys.argv[2]) if len(sys.argv) > 2 else 38
 lines = open(path).read().splitlines()
 start = next(i for i, l in enumerate(lines) if l.startswith('"ID"'))
-rows = [r for r in csv.DictReader(lines[start:]) if 'adec::' in r['Kernel Name'] and 'replicate' not in r['Kernel Name']]
+rows = [r for r in csv.DictReader(lines[start:]) if 'adec::' in r['Kernel Name'] and 'replicate' not in r['Kernel Name'] and 'mma_probe' not in r['Kernel Name']]
 last = rows[-n:]
 tot = sum(float(r['Metric Value']) for r in last)
 print(f"{len(rows)} adec launches in file; last {n}: total {tot/1e6:.3f} ms")

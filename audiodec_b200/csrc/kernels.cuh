@@ -98,8 +98,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // pipe, bounds the narrow layers; ex2.approx(x*log2e) - 1 is 4 instructions and within 2.4e-7 ABSOLUTE of expm1 on
 // (-inf, 0] (2^-22 relative error of ex2.approx on a value <= 1) - the same order as the fp32 rounding of the O(1)
 // activations it is summed with.  Parity margins: tests/test_layers_gpu.py (1e-5 on a fused unit), golden indices.
+// __expf() wraps ex2.approx in a denormal-range fix-up (FSETP -126 / FMUL 0.5 / FMUL square: 8 instructions per ELU, 18 % of all
+// instructions of the C = 32 unit in the round-2 ncu capture); ex2.approx.ftz is the bare MUFU.EX2 and gives the same ELU bit for bit:
+// where the two differ (x log2(e) < -126) exp(x) is below 2^-126 and exp(x) - 1 rounds to -1 either way.
 __device__ __forceinline__ float act_elu(float v) {
-    const float e = __expf(v) - 1.0f;
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * 1.4426950408889634f));
+    e -= 1.0f;
     return v > 0.f ? v : e;
 }
 __device__ __forceinline__ float act_lrelu(float v, float s) { return v > 0.f ? v : v * s; }

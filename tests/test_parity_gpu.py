@@ -61,6 +61,17 @@ def test_symad_oneshot_golden(golden_dir, symad_sd, conv_path):
     np.testing.assert_allclose(y.numpy(), g["y"], atol=WAVE_TOL)
 
 
+def test_whole_piece_partials_mode_golden(golden_dir, symad_sd, monkeypatch):
+    """ADEC_GSPAN=1 (experiment, off by default): one TMEM partial per 32-channel piece instead of per tap pair - 14-step accumulation
+    chains, a single issuing warp.  Must still meet the bar on the golden clip (it roughly doubles the rounding error: DESIGN.md 4.0)."""
+    monkeypatch.setenv("ADEC_GSPAN", "1")
+    g = np.load(os.path.join(golden_dir, "symad_oneshot.npz"))
+    tx, rx, dec, _ = _codec(symad_sd)
+    z, idx, zq, y = _run(tx, rx, dec, torch.from_numpy(g["x"]))
+    np.testing.assert_array_equal(idx.numpy(), g["idx"])
+    np.testing.assert_allclose(y.numpy(), g["y"], atol=WAVE_TOL)
+
+
 def test_symad_stream_chunks_golden(golden_dir, symad_sd, conv_path):
     g = np.load(os.path.join(golden_dir, "symad_stream.npz"))
     tx, rx, dec, _ = _codec(symad_sd)

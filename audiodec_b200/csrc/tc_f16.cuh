@@ -90,6 +90,9 @@ template <int NT, int PREC> struct TcfCfg {
     // 10.5 stalls per issue, issue slots 22 % busy).  The fused NT = 128 unit (64 + 64 live accumulators) keeps 4 producer warps and
     // 128 registers.  (setmaxnreg re-balancing was tried: ptxas caps the control / producer sections as asked but does not give the
     // drain section more than the launch bound, so it only added spills.)
+#ifndef ADEC_PLAIN_TEAMS
+#define ADEC_PLAIN_TEAMS 2       // producer teams of the un-fused launches (1 = all 8 warps on one piece, the round-1 arrangement)
+#endif
 #ifndef ADEC_NT128_PLAIN_NPROD
 #define ADEC_NT128_PLAIN_NPROD 256
 #endif
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], NPROD); mbar_init(&w_empty[i], NW); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], (!FUSE && NPROD == 256) ? NPROD / ADEC_PLAIN_TEAMS : NPROD); mbar_init(&w_empty[i], NW); }
         for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
         for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], NW);
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
@@ -398,12 +401,21 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         // into a second register set - 200-500 B of spills per thread, 10.4 -> 17.3 ms per step - and a fully software-pipelined batch
         // sequence with one general row resolver - twice the instructions, 11.3 -> 13.3 ms.  The producers are issue- and register-
         // bound, not load-latency-bound.)
+        // Plain (un-fused) launches: the 8 producer warps work as TWO TEAMS of 4 that build alternate window pieces concurrently.  The
+        // timeline of the 1x1 / strided / transposed convs showed one piece every ~2600 cycles (a batch of loads, their latency, the
+        // conversion) against 400-800 cycles of MMAs per piece: these layers are bound by the producers' load latency, and two pieces in
+        // flight hide half of it.  (Safe with any a.n_wbuf >= 2: pieces are consumed in order, so passing the wait for piece q implies every
+        // piece <= q - n_wbuf was consumed and no waiter is ever two barrier phases behind.)
         const int pt = tid - 128;
+        constexpr int NTEAM = (!FUSE && NPROD == 256) ? ADEC_PLAIN_TEAMS : 1, TPROD = NPROD / NTEAM;
+        const int team = pt / TPROD, ptl = pt - team * TPROD;
+        int pcnt = 0;                              // running piece counter (team = pcnt % NTEAM)
         ADEC_TL_DECL(4);
         int wb = 0, wround = 0;                    // window piece counter wp = wround * n_wbuf + wb
-        constexpr int RPP = NPROD / KB;            // window rows per pass
-        constexpr int UNR = NPROD == 128 ? 5 : 3;  // rows in flight per thread (2 x 128-bit loads each): one pass covers 160 / 192 rows
-        const int c8 = pt & (KB - 1), m0 = pt >> 2;
+        constexpr int RPP = TPROD / KB;            // window rows per pass
+        constexpr int UNR = TPROD == 128 ? 5 : 3;  // rows in flight per thread (one 256-bit load each): one pass covers 160 / 192 rows
+        constexpr int UNR_E = (NTEAM > 1) ? 2 : UNR;   // edge pieces (rare): fewer rows per batch where the interior batch already takes the registers
+        const int c8 = ptl & (KB - 1), m0 = ptl >> 2;
         const bool halves = a.RG > 1 && a.Cin < 8; // a 4-channel strided conv: the two halves of a block are different x~ rows
         for (TileIter it(blockIdx.x, gridDim.x, n_xtiles, n_ytiles); it.tile < n_tiles; it.next(gridDim.x)) {
             const int xt = it.xt, y = it.y, b = it.b;
@@ -412,12 +424,13 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
             const int j0 = xt * TT;
             const float* xg = a.x + (long long)b * a.x_bs + g * a.x_goff;
             const float* sg = a.st_in + (long long)b * a.P * a.st_ld + g * a.st_goff;
-            for (int p = 0; p < a.n_pieces; ++p) {
+            for (int p = 0; p < a.n_pieces; ++p, ++pcnt) {
                 const int buf = wb;
                 if (pt == 0) ADEC_TL(8, p);
                 const uint32_t wpar = (uint32_t)(wround - 1) & 1u;
                 bool waited = wround == 0;
                 if (++wb == a.n_wbuf) { wb = 0; ++wround; }
+                if (NTEAM > 1 && pcnt % NTEAM != team) continue;      // the other team's piece
                 unsigned char* hi = wbuf0 + (size_t)buf * win_b + (size_t)c8 * wrp * 16;
                 unsigned char* lo = hi + (size_t)KB * wrp * 16;
                 const int q = p * CP + c8 * 8;
@@ -446,11 +459,11 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 } else {
                     // edge piece: rows from the causal state (stored post-activation), the chunk, or beyond its end (zeros)
                     int ci2 = ci + 4;
-                    for (int mb = m0; mb < wrows; mb += RPP * UNR) {
-                        float4 u[UNR], v[UNR];
+                    for (int mb = m0; mb < wrows; mb += RPP * UNR_E) {
+                        float4 u[UNR_E], v[UNR_E];
                         unsigned act = 0u;
 #pragma unroll
-                        for (int k = 0; k < UNR; ++k) {
+                        for (int k = 0; k < UNR_E; ++k) {
                             const int m = mb + k * RPP;
                             u[k] = v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
                             if (m < wrows) {
@@ -484,7 +497,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                         }
                         if (!waited) { mbar_wait(&w_empty[buf], wpar, 500); waited = true; }
 #pragma unroll
-                        for (int k = 0; k < UNR; ++k) {
+                        for (int k = 0; k < UNR_E; ++k) {
                             const int m = mb + k * RPP;
                             if (m < wrows) {
                                 float4 x0 = u[k], x1 = v[k];

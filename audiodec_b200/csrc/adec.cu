@@ -247,6 +247,7 @@ struct adec_handle {
     int engine = 2;               // ADEC_CONV_PATH: 2 = f16 (tcgen05 kind::f16, default), 1 = tf32 (round-1 3xTF32), 0 = ffma (CUDA cores)
     bool use_tc = true;           // any tensor-core engine
     bool bf16 = false;            // cfg.compute_dtype == 1: bf16 operands (HiFi-GAN vocoder, f16 engine only)
+    int plain_teams = 2;          // ADEC_PLAIN_TEAMS=1: one producer team on the un-fused launches (A/B)
     int gspan = 0;                // ADEC_GSPAN: accumulation span of the f16 engine (ConvArgs::gspan)
     int dbg_flags = 0;
     int dbg_wdiv = 0;             // ADEC_DBG_WDIV (timing experiments, wrong results)
@@ -717,6 +718,7 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.mid_act = op.mid_act;
             a.hist_rep = (rc.offline && op.up > 1) ? 1 : 0;
             a.w_scale = op.w_scale; a.w2_scale = op.w2_scale; a.err = h->d_err; a.dbg_wdiv = h->dbg_wdiv; a.dbg_flags = h->dbg_flags;
+            a.teams = h->plain_teams;
             a.gspan = (h->gspan == 1 || (h->gspan == 2 && op.tcf && op.tcf->NT >= 128) || (h->gspan == 3 && op.tcf && op.tcf->NT >= 64)) ? 1 : 0;
 #ifdef ADEC_TIMELINE
             // debug build: record CTA 1's event timeline of the op named by ADEC_TIMELINE_OP on its 4th launch, dump it to ADEC_TIMELINE_OUT
@@ -1184,6 +1186,7 @@ int adec_create(const adec_config* cfg, int device, adec_handle** out) {
     h->use_tc = h->engine != 0;
     if (const char* sr = getenv("ADEC_STACK_ROWS")) h->stack_rows = atoi(sr) != 0;
     if (const char* gs = getenv("ADEC_GSPAN")) h->gspan = atoi(gs);
+    if (const char* pt = getenv("ADEC_PLAIN_TEAMS")) h->plain_teams = atoi(pt) == 1 ? 1 : 2;
     if (const char* wd = getenv("ADEC_DBG_WDIV")) h->dbg_wdiv = atoi(wd);
     if (const char* df = getenv("ADEC_DBG_FLAGS")) h->dbg_flags = atoi(df);
     if (const char* kt = getenv("ADEC_KTRACE")) {

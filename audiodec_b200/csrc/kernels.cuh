@@ -162,6 +162,7 @@ struct ConvArgs {
     // tcgen05 kind::f16 engine (tc_f16.cuh): weights are stored times a power of two; the drain warps multiply the sums by these
     float w_scale, w2_scale;
     int n_wbuf;          // window buffers in shared memory (2..4)
+    int teams;           // tc_f16, un-fused launches: 2 = the 8 producer warps build alternate window pieces as two teams of 4, 1 = one team
     int gspan;           // tc_f16: 1 = one TMEM partial per 32-channel piece (all taps) instead of one per tap pair
     // stacked rows: when a stream contributes fewer rows than a 128-row tile, the tiles run over ONE row space in which stream s owns
     // rows [s * stack_L, (s + 1) * stack_L), stack_L = Tout + (Ktaps - 1) * dil: local rows >= Tout are the receptive-field overlap into

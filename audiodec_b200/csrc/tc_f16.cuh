@@ -90,9 +90,6 @@ template <int NT, int PREC> struct TcfCfg {
     // 10.5 stalls per issue, issue slots 22 % busy).  The fused NT = 128 unit (64 + 64 live accumulators) keeps 4 producer warps and
     // 128 registers.  (setmaxnreg re-balancing was tried: ptxas caps the control / producer sections as asked but does not give the
     // drain section more than the launch bound, so it only added spills.)
-#ifndef ADEC_PLAIN_TEAMS
-#define ADEC_PLAIN_TEAMS 2       // producer teams of the un-fused launches (1 = all 8 warps on one piece, the round-1 arrangement)
-#endif
 #ifndef ADEC_NT128_PLAIN_NPROD
 #define ADEC_NT128_PLAIN_NPROD 256
 #endif
@@ -239,7 +236,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], (!FUSE && NPROD == 256) ? NPROD / ADEC_PLAIN_TEAMS : NPROD); mbar_init(&w_empty[i], NW); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], (!FUSE && NPROD == 256) ? NPROD / a.teams : NPROD); mbar_init(&w_empty[i], NW); }
         for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
         for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], NW);
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
@@ -407,14 +404,16 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         // flight hide half of it.  (Safe with any a.n_wbuf >= 2: pieces are consumed in order, so passing the wait for piece q implies every
         // piece <= q - n_wbuf was consumed and no waiter is ever two barrier phases behind.)
         const int pt = tid - 128;
-        constexpr int NTEAM = (!FUSE && NPROD == 256) ? ADEC_PLAIN_TEAMS : 1, TPROD = NPROD / NTEAM;
-        const int team = pt / TPROD, ptl = pt - team * TPROD;
-        int pcnt = 0;                              // running piece counter (team = pcnt % NTEAM)
+        constexpr bool TEAMS = !FUSE && NPROD == 256;             // kernels that can run two producer teams (a.teams = 1 or 2, ADEC_PLAIN_TEAMS)
+        const int nteam = TEAMS ? a.teams : 1, tprod = NPROD / nteam;
+        const int team = pt / tprod, ptl = pt - team * tprod;
+        int pcnt = 0;                              // running piece counter (team = pcnt % nteam)
         ADEC_TL_DECL(4);
         int wb = 0, wround = 0;                    // window piece counter wp = wround * n_wbuf + wb
-        constexpr int RPP = TPROD / KB;            // window rows per pass
-        constexpr int UNR = TPROD == 128 ? 5 : 3;  // rows in flight per thread (one 256-bit load each): one pass covers 160 / 192 rows
-        constexpr int UNR_E = (NTEAM > 1) ? 2 : UNR;   // edge pieces (rare): fewer rows per batch where the interior batch already takes the registers
+        const int RPP = tprod / KB;                // window rows per pass
+        constexpr int UNR = (TEAMS || NPROD == 128) ? 5 : 3;   // rows in flight per thread (one 256-bit load each): a pass covers >= 160 rows
+        constexpr int UNR_E = NPROD == 128 ? 5 : (TEAMS ? 2 : 3);   // edge pieces (rare, or every piece of a stacked launch): fewer rows per batch where
+                                                                    // the interior batch already takes the registers (3 here spills 120 B instead of 40)
         const int c8 = ptl & (KB - 1), m0 = ptl >> 2;
         const bool halves = a.RG > 1 && a.Cin < 8; // a 4-channel strided conv: the two halves of a block are different x~ rows
         for (TileIter it(blockIdx.x, gridDim.x, n_xtiles, n_ytiles); it.tile < n_tiles; it.next(gridDim.x)) {
@@ -430,7 +429,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 const uint32_t wpar = (uint32_t)(wround - 1) & 1u;
                 bool waited = wround == 0;
                 if (++wb == a.n_wbuf) { wb = 0; ++wround; }
-                if (NTEAM > 1 && pcnt % NTEAM != team) continue;      // the other team's piece
+                if (TEAMS && nteam > 1 && (pcnt & 1) != team) continue;      // the other team's piece
                 unsigned char* hi = wbuf0 + (size_t)buf * win_b + (size_t)c8 * wrp * 16;
                 unsigned char* lo = hi + (size_t)KB * wrp * 16;
                 const int q = p * CP + c8 * 8;

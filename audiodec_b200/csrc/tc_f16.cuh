@@ -90,6 +90,9 @@ template <int NT, int PREC> struct TcfCfg {
     // 10.5 stalls per issue, issue slots 22 % busy).  The fused NT = 128 unit (64 + 64 live accumulators) keeps 4 producer warps and
     // 128 registers.  (setmaxnreg re-balancing was tried: ptxas caps the control / producer sections as asked but does not give the
     // drain section more than the launch bound, so it only added spills.)
+#ifndef ADEC_UNR_E
+#define ADEC_UNR_E 2
+#endif
 #ifndef ADEC_NT128_PLAIN_NPROD
 #define ADEC_NT128_PLAIN_NPROD 256
 #endif
@@ -412,7 +415,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         int wb = 0, wround = 0;                    // window piece counter wp = wround * n_wbuf + wb
         const int RPP = tprod / KB;                // window rows per pass
         constexpr int UNR = (TEAMS || NPROD == 128) ? 5 : 3;   // rows in flight per thread (one 256-bit load each): a pass covers >= 160 rows
-        constexpr int UNR_E = NPROD == 128 ? 5 : (TEAMS ? 2 : 3);   // edge pieces (rare, or every piece of a stacked launch): fewer rows per batch where
+        constexpr int UNR_E = NPROD == 128 ? 5 : (TEAMS ? ADEC_UNR_E : 3);   // edge pieces (rare, or every piece of a stacked launch): fewer rows per batch where
                                                                     // the interior batch already takes the registers (3 here spills 120 B instead of 40)
         const int c8 = ptl & (KB - 1), m0 = ptl >> 2;
         const bool halves = a.RG > 1 && a.Cin < 8; // a 4-channel strided conv: the two halves of a block are different x~ rows

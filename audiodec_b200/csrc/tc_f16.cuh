@@ -90,6 +90,9 @@ template <int NT, int PREC> struct TcfCfg {
     // 10.5 stalls per issue, issue slots 22 % busy).  The fused NT = 128 unit (64 + 64 live accumulators) keeps 4 producer warps and
     // 128 registers.  (setmaxnreg re-balancing was tried: ptxas caps the control / producer sections as asked but does not give the
     // drain section more than the launch bound, so it only added spills.)
+#ifndef ADEC_FUSE_TEAMS
+#define ADEC_FUSE_TEAMS 0        // 1 = the fused NT = 32 / 64 units also run two producer teams (A/B)
+#endif
 #ifndef ADEC_UNR_E
 #define ADEC_UNR_E 2
 #endif
@@ -239,7 +242,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], (!FUSE && NPROD == 256) ? NPROD / a.teams : NPROD); mbar_init(&w_empty[i], NW); }
+        for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], ((!FUSE || ADEC_FUSE_TEAMS) && NPROD == 256) ? NPROD / a.teams : NPROD); mbar_init(&w_empty[i], NW); }
         for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
         for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], NW);
         for (int i = 0; i < NPB; ++i) { mbar_init(&p_full[i], 1); mbar_init(&p_empty[i], 128 * NDG); }
@@ -407,7 +410,7 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
         // flight hide half of it.  (Safe with any a.n_wbuf >= 2: pieces are consumed in order, so passing the wait for piece q implies every
         // piece <= q - n_wbuf was consumed and no waiter is ever two barrier phases behind.)
         const int pt = tid - 128;
-        constexpr bool TEAMS = !FUSE && NPROD == 256;             // kernels that can run two producer teams (a.teams = 1 or 2, ADEC_PLAIN_TEAMS)
+        constexpr bool TEAMS = (!FUSE || ADEC_FUSE_TEAMS) && NPROD == 256;             // kernels that can run two producer teams (a.teams = 1 or 2, ADEC_PLAIN_TEAMS)
         const int nteam = TEAMS ? a.teams : 1, tprod = NPROD / nteam;
         const int team = pt / tprod, ptl = pt - team * tprod;
         int pcnt = 0;                              // running piece counter (team = pcnt % nteam)

@@ -153,8 +153,21 @@ cudaError_t launch_tcf(const ConvArgs& a, int n_xtiles, int n_ytiles, int n_tile
         configured[dev] = true;
     }
     if (smem_bytes > kMaxDyn) return cudaErrorInvalidConfiguration;
-    kern<<<n_ctas, TcfCfg<NT, PREC>::threads(F), smem_bytes, s>>>(a, n_xtiles, n_ytiles, n_tiles);
-    return cudaGetLastError();
+    // Programmatic dependent launch: the next launch's CTAs may start (barrier init, TMEM allocation, first weight stages - weights are
+    // constants) while the tail of the previous kernel of the stream is still running; its producer and drain warps execute
+    // griddepcontrol.wait before they touch any activation or state (tc_f16.cuh), which blocks until the previous grid has completed.
+    static const bool pdl = [] { const char* e = getenv("ADEC_PDL"); return !e || atoi(e) != 0; }();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)n_ctas);
+    cfg.blockDim = dim3((unsigned)TcfCfg<NT, PREC>::threads(F));
+    cfg.dynamicSmemBytes = (size_t)smem_bytes;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a, n_xtiles, n_ytiles, n_tiles);
 }
 typedef size_t (*TcfSmemFn)(int, bool);
 typedef int (*TcfWbufFn)(int, bool);

@@ -256,6 +256,10 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    // programmatic dependent launch (adec.cu launch_tcf): everything above - and the weight stream below, weights being constants - may
+    // overlap the previous kernel's tail; the warps that read activations / state / skip tensors or write outputs wait for that grid first
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (warp >= 4) asm volatile("griddepcontrol.wait;" ::: "memory");
     if (warp == 0) {
         // ------------------------------------------------ weight producer: one bulk copy per group (1 or 2 taps)
         if (lane == 0) {

@@ -1,5 +1,8 @@
 #!/bin/bash
-# usage: tools/gpu_timeline.sh <tag> <op name> ...   (needs audiodec_b200/lib/libaudiodec_b200_tl.so built with -DADEC_TIMELINE)
+# usage: tools/gpu_timeline.sh <tag> <op name> ...
+# first build the instrumented library here (it travels with gpurun):
+#   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC -shared -DADEC_TIMELINE \
+#        -o audiodec_b200/lib/libaudiodec_b200_tl.so audiodec_b200/csrc/adec.cu
 OUT=gpurun_out/$1; shift; mkdir -p $OUT
 export ADEC_LIB_PATH=$PWD/audiodec_b200/lib/libaudiodec_b200_tl.so
 for OP in "$@"; do

@@ -732,10 +732,10 @@ int run_ops(adec_handle* h, std::vector<Op>& ops, const RunCtx& rc, int T_in, in
             a.hist_rep = (rc.offline && op.up > 1) ? 1 : 0;
             a.w_scale = op.w_scale; a.w2_scale = op.w2_scale; a.err = h->d_err; a.dbg_wdiv = h->dbg_wdiv; a.dbg_flags = h->dbg_flags;
             a.teams = h->plain_teams;
-            // bf16-operand launches (the vocoder's reduced-precision mode) at NT = 128 accumulate a whole 32-channel piece per TMEM partial: their
-            // groups are 4 MMAs, so the TMEM -> register round trip per group is what they wait for, and a 22-step accumulation chain's
-            // truncation (3e-7) is far below bf16 operand rounding (measured: blocks.1 convs 0.84 / 0.98 -> 0.72 / 0.80 ms at batch 128)
-            const bool bf16_span = op.tcf && op.tcf->prec == 1 && op.tcf->NT >= 128 && h->gspan == 0;
+            // bf16-operand launches (the vocoder's reduced-precision mode) accumulate a whole 32-channel piece per TMEM partial: their groups
+            // are 4 MMAs, so the TMEM -> register round trip per group is what they wait for, and a 22-step accumulation chain's truncation
+            // (3e-7) is far below bf16 operand rounding (measured at batch 128: 43.9 -> 41.5 ms per step, blocks.3.convs2 2.06 -> 1.72 ms)
+            const bool bf16_span = op.tcf && op.tcf->prec == 1 && h->gspan == 0;
             a.gspan = (bf16_span || h->gspan == 1 || (h->gspan == 2 && op.tcf && op.tcf->NT >= 128) || (h->gspan == 3 && op.tcf && op.tcf->NT >= 64)) ? 1 : 0;
 #ifdef ADEC_TIMELINE
             // debug build: record CTA 1's event timeline of the op named by ADEC_TIMELINE_OP on its 4th launch, dump it to ADEC_TIMELINE_OUT

@@ -234,14 +234,14 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
     // TMEM partials per tile.  gspan = 0: one partial per group (4 main accumulation steps, then round-to-nearest register adds);
     // gspan = 1: one partial per 32-channel PIECE (all its taps: 14 main steps at K = 7) and one for the whole 1x1 conv - 3.5x fewer
     // TMEM -> register round trips, which bound the wide layers (timeline: ~2400 cycles of tcgen05.ld latency per partial at NT = 128
-    // against 816 cycles of MMAs per group); a single warp issues in that mode so every accumulator sees its MMAs in program order.
+    // against 816 cycles of MMAs per group); a partial's MMAs all come from one issuer warp (partials round robin over the warps).
     const bool span = a.gspan != 0;
     const int n_g1 = span ? a.n_pieces : a.n_pieces * gpp;
     const int n_g2 = FUSE ? (span ? 1 : NT / CP) : 0;
     const int n_s2 = FUSE ? NT / CP : 0;                          // weight stages of the 1x1 conv
 
     if (tid == 0) {
-        for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+        for (int s = 0; s < S; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], a.gspan ? NW : 1); }
         for (int i = 0; i < 4; ++i) { mbar_init(&w_full[i], ((!FUSE || ADEC_FUSE_TEAMS) && NPROD == 256) ? NPROD / a.teams : NPROD); mbar_init(&w_empty[i], NW); }
         for (int i = 0; i < MB; ++i) mbar_init(&m_full[i], HALF ? 256 : 128);
         for (int i = 0; i < 2; ++i) mbar_init(&m_empty[i], NW);
@@ -367,7 +367,12 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 const uint32_t a_lo = a_hi + (uint32_t)KB * lbo1;
                 for (int t0 = 0; t0 < a.Ktaps; t0 += 2, ++c) {
                     const bool first = !span || t0 == 0, last = !span || t0 + 2 >= a.Ktaps;
-                    if (span ? mw == 0 : c % NW == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)t0 * tap_step, tap_step, a.Ktaps - t0 >= 2 ? 2 : 1, first, last);
+                    // span mode: a partial's stages all belong to the warp that owns the partial (qc % NW: the MMAs of one accumulator must come
+                    // from one thread, in order).  The other issuer warps wait on every weight stage too and acknowledge it on b_empty (count NW
+                    // in this mode), so a stage slot is not refilled before EVERY issuer warp has seen its phase: no waiter can fall two
+                    // phases behind (a first version without the acknowledgement dead-locked at batch scale exactly that way)
+                    if (span ? qc % NW == mw : c % NW == mw) issue_group(a_hi, a_lo, lbo1, (uint32_t)t0 * tap_step, tap_step, a.Ktaps - t0 >= 2 ? 2 : 1, first, last);
+                    else if (span) { mbar_wait(&b_full[c % S], (c / S) & 1, 300); if (lane == 0) mbar_arrive(&b_empty[c % S]); __syncwarp(); }
                     if (last) ++qc;
                 }
                 if (elect_one()) umma_commit(&w_empty[buf]);
@@ -381,7 +386,8 @@ __global__ void __launch_bounds__(TcfCfg<NT, PREC>::threads(FUSE), 1) tc_conv_f1
                 const uint32_t m_hi = mbuf_u + (uint32_t)mb * Cfg::MID_BYTES;
                 {
                     const bool first = !span || p == 0, last = !span || p == NT / CP - 1;
-                    if (span ? mw == 0 : c % NW == mw) issue_group(m_hi, m_hi + (uint32_t)KB * lbo2, lbo2, 0u, 0u, 1, first, last);
+                    if (span ? qc % NW == mw : c % NW == mw) issue_group(m_hi, m_hi + (uint32_t)KB * lbo2, lbo2, 0u, 0u, 1, first, last);
+                    else if (span) { mbar_wait(&b_full[c % S], (c / S) & 1, 300); if (lane == 0) mbar_arrive(&b_empty[c % S]); __syncwarp(); }
                     if (last) ++qc;
                 }
                 // buffer mb is free for piece mp + MB, which drain group (mp + MB) % NDG writes: signal THAT group's barrier

@@ -63,7 +63,7 @@ def test_symad_oneshot_golden(golden_dir, symad_sd, conv_path):
 
 def test_whole_piece_partials_mode_golden(golden_dir, symad_sd, monkeypatch):
     """ADEC_GSPAN=1 (experiment, off by default): one TMEM partial per 32-channel piece instead of per tap pair - 14-step accumulation
-    chains, a single issuing warp.  Must still meet the bar on the golden clip (it roughly doubles the rounding error: DESIGN.md 4.0)."""
+    chains (each partial issued by one warp, partials round robin).  Must still meet the bar on the golden clip (it roughly doubles the rounding error: DESIGN.md 4.0)."""
     monkeypatch.setenv("ADEC_GSPAN", "1")
     g = np.load(os.path.join(golden_dir, "symad_oneshot.npz"))
     tx, rx, dec, _ = _codec(symad_sd)

@@ -229,3 +229,18 @@ def test_demo_file_cli_refuses_cpu_and_missing_input(tmp_path):
         demo_file.main(["--model", "no_such_model", "-i", "x.wav", "-o", "y.wav"])
     with pytest.raises(ValueError):
         demo_file.main(["--model", "vctk_v1", "-i", str(tmp_path / "missing.wav"), "-o", "y.wav"])
+
+
+def test_time_pairing_identity():
+    """Design check for DESIGN.md section 8 item 1 (tools/pairing_math.py): the paired-weight GEMM over de-interleaved windows equals the
+    dilated causal conv it replaces, for the dilations and kernel sizes of the symAD units and the HiFi-GAN blocks."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("pairing_math", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "pairing_math.py"))
+    pm = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pm)
+    rng = np.random.default_rng(1)
+    for (K, d, C, T) in ((7, 1, 16, 64), (7, 3, 16, 60), (7, 9, 16, 72), (11, 5, 8, 40)):
+        W = rng.standard_normal((K, C, C)).astype(np.float32)
+        xt = rng.standard_normal((T + (K - 1) * d, C)).astype(np.float32)
+        np.testing.assert_allclose(pm.paired(xt, W, d), pm.direct(xt.astype(np.float64), W.astype(np.float64), d), atol=1e-9)

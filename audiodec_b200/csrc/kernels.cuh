@@ -77,8 +77,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* b, uint32_t parity, int tag 
 #endif
         }
         if (clock64() - t0 > ADEC_WATCHDOG_CYCLES) {
+#ifdef ADEC_WATCHDOG_PRINT
             printf("adec: mbarrier wait timed out: tag %d parity %u block (%d,%d,%d) thread %d\n", tag, parity, blockIdx.x, blockIdx.y,
                    blockIdx.z, threadIdx.x);
+#endif
             __trap();
         }
     }
